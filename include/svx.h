@@ -1,0 +1,217 @@
+/*
+ * include/svx.h — C ABI of libsvx.so, the B200 (sm_100a) implementation of Speech-Vecalign's
+ * segment-alignment hot path (svecalign/vecalign/dp_core.pyx + the numeric helpers of
+ * svecalign/vecalign/dp_utils.py).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross this boundary.
+ *   - Every pointer named *_d / inside a job struct is a DEVICE pointer owned by the caller;
+ *     kernels never allocate.  `stream` is a cudaStream_t passed as void*.
+ *   - Every launcher takes an array of job descriptors that lives in DEVICE memory plus the same
+ *     array on the HOST (`jobs_h`, used only to size the grid); a single document pair is a batch of
+ *     one job.  Work for different jobs is independent: no collective, no cross-job ordering.
+ *   - Return value: 0 = OK, otherwise an SVX_ERR_* code; svx_last_error_string() explains it.
+ *     Device-side failures (search path leaves the band, "-42" backpointer reached — the
+ *     reference's 'traceback bug' / IndexError conditions, dp_utils.py:123-124) are reported per
+ *     job in SvxBandJob.status_d / SvxDenseJob.status_d.
+ *   - All fp32 dot products of the cost kernels are evaluated in the reference's order
+ *     (sequential multiply-then-add over the embedding dimension, no FMA) when mode ==
+ *     SVX_COST_EXACT, so costs are bit-identical to dp_core.pyx given identical inputs;
+ *     SVX_COST_FAST contracts to FMA (same order) and is within 2e-6 absolute.
+ *
+ * Each entry point cites the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef SVX_H_
+#define SVX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVX_VERSION 100
+
+#if defined(__GNUC__)
+#define SVX_API __attribute__((visibility("default")))
+#else
+#define SVX_API
+#endif
+
+/* error codes */
+#define SVX_OK 0
+#define SVX_ERR_CUDA 1        /* a CUDA runtime call failed */
+#define SVX_ERR_ARG 2         /* invalid argument (shape, dim, null pointer)  */
+#define SVX_ERR_UNSUPPORTED 3 /* valid in the reference but outside this build's limits */
+
+/* cost arithmetic */
+#define SVX_COST_EXACT 0
+#define SVX_COST_FAST 1
+
+/* per-job device status bits (status_d) */
+#define SVX_ST_OK 0
+#define SVX_ST_LEFT_BAND 1   /* traceback left the band (reference: IndexError / wrap-around)  */
+#define SVX_ST_NO_BACKPTR 2  /* reached a node whose backpointer is the -42 sentinel          */
+#define SVX_ST_OVERFLOW 4    /* output record capacity exceeded                               */
+
+#define SVX_BP_NONE 255      /* uint8 backpointer for the reference's (-42,-42) sentinel      */
+#define SVX_MAX_TYPES 126    /* alignment types per job incl. the two deletion types          */
+
+/* ------------------------------------------------------------------------------------------------
+ * Row blocks: a (K*n, dim) fp32 matrix of embedding rows.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxRows {
+    float *ptr;      /* (nrows, dim) row-major, 16-byte aligned                        */
+    int64_t nrows;
+} SvxRows;
+
+/* Replaces dp_utils.make_norm1 (dp_utils.py:32-40): in place v /= sqrt(sum(v*v)) + 1e-5, fp32,
+ * with numpy's pairwise summation order (bit-identical to numpy >= 2.0).  dim in
+ * {128,256,512,1024}. */
+SVX_API int svx_normalize_rows(const SvxRows *jobs_d, const SvxRows *jobs_h, int njobs, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Downsample: replaces dp_utils.downsample_vectors (dp_utils.py:362-378).
+ * out[o,j,:] = in[o,2j,:] + in[o,2j+1,:]; minus the per-overlap mean row (sequential fp32 row
+ * accumulation = np.mean(axis=0)); rows normalised as above.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxDownJob {
+    const float *in;   /* (k, n, dim)                                   */
+    float *out;        /* (k, n/2, dim)                                 */
+    float *mean;       /* (k, dim) scratch: receives the mean rows      */
+    int32_t k, n;
+} SvxDownJob;
+SVX_API int svx_downsample(const SvxDownJob *jobs_d, const SvxDownJob *jobs_h, int njobs, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sample norms: replaces dp_utils.compute_norms (dp_utils.py:326-359).
+ * norms[o,i] = 1 - vecs[o,i,:] . mean_s(samples_s), samples = rows `idx[o']` of overlap o' of the
+ * OTHER side (host RNG draws, np.random.choice order of :346).  The reference computes the same
+ * quantity with an sgemm followed by an fp32 mean (order not reproducible across CPUs); this
+ * GEMV form accumulates in fp64 and agrees to <= 2 ulp (tests state the tolerance).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxNormJob {
+    const float *vecs;     /* (k, n, dim) rows to be normed                                 */
+    const float *other;    /* (ko, no, dim) side the samples are drawn from                 */
+    const int32_t *idx;    /* (ko, per) sampled row ids in [0, no)                          */
+    double *mbar;          /* (dim) scratch: mean sample vector                             */
+    float *norms;          /* (k, n) output                                                 */
+    int32_t k, n, ko, no, per;
+} SvxNormJob;
+SVX_API int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs_h, int njobs, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampled pair scores + deletion penalty: replaces dp_core.score_path (dp_core.pyx:143-161) and
+ * dp_utils.DeletionKnob / make_del_knob (dp_utils.py:43-79, 278-323).
+ * scores[i] = 2(1 - e[xi].f[yi]) / (ne[xi] + nf[yi])  (fp32 denominator, no 1e-6).
+ * If xi == NULL the full ne x nf grid is scored row-major (the reference's no-RNG branch).
+ * svx_del_knob reproduces numpy's histogram(1000 bins, density) / cumsum / searchsorted / interp
+ * arithmetic bit-for-bit and writes del_penalty (fp64).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxScoreJob {
+    const float *e;        /* (ne, dim) overlap-0 rows of side 0                */
+    const float *f;        /* (nf, dim) overlap-0 rows of side 1                */
+    const float *norm_e;   /* (ne)                                              */
+    const float *norm_f;   /* (nf)                                              */
+    const int32_t *xi;     /* (nsamp) or NULL for the full grid                 */
+    const int32_t *yi;     /* (nsamp) or NULL                                   */
+    float *scores;         /* (nsamp) output                                    */
+    double *del_penalty;   /* (1) output of svx_del_knob                        */
+    int32_t ne, nf, nsamp;
+} SvxScoreJob;
+SVX_API int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, int dim, int mode,
+                    void *stream);
+SVX_API int svx_del_knob(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, double frac, void *stream);
+/* Host twin of svx_del_knob (same arithmetic compiled for the CPU; used by the not-gpu tests). */
+SVX_API int svx_host_del_knob(const float *scores, int n, double frac, double *del_penalty);
+
+/* ------------------------------------------------------------------------------------------------
+ * Coarsest level: dense costs + 3-way DP + traceback + search path of the next finer level.
+ * Replaces dp_core.make_dense_costs (dp_core.pyx:36-77), dp_core.dense_dp (:79-141),
+ * dp_utils.dense_traceback (dp_utils.py:146-174) and, for the path, upsample_alignment /
+ * extend_alignments / alignment_to_search_path / append_slant (dp_utils.py:177-275).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxDenseJob {
+    const float *v0;           /* (s0, dim) overlap-0 rows                               */
+    const float *v1;           /* (s1, dim)                                              */
+    const float *n0;           /* (s0)                                                   */
+    const float *n1;           /* (s1)                                                   */
+    float *costs;              /* (s0, s1) output of svx_dense_costs                     */
+    const double *del_penalty; /* (1); narrowed to fp32 as dense_dp(float pen) does      */
+    uint8_t *bp;               /* (s0+1, s1+1) backpointers 0/1/2, 4 at the origin       */
+    double *csum;              /* (s0+1, s1+1) or NULL (debug/parity only)               */
+    int32_t *ypath;            /* (path_len) y of the search path of the target level    */
+    int32_t *status_d;         /* (1)                                                    */
+    int32_t s0, s1;
+    int32_t t0, t1;            /* sizes of the target (finer) level                      */
+    int32_t upsample;          /* 1: target is the next finer level (x2 + extension);    */
+                               /* 0: same level (max_depth == 0)                         */
+    int32_t path_len;          /* A of the target level (svx_path_len)                   */
+} SvxDenseJob;
+SVX_API int svx_dense_costs(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, int mode,
+                    void *stream);
+SVX_API int svx_dense_dp(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, void *stream);
+
+/* Length of the search path built from a coarse alignment of (c0,c1) segments for a target level
+ * of (t0,t1) segments (upsample=1), or from a same-size dense alignment (upsample=0). */
+SVX_API int svx_path_len(int c0, int c1, int t0, int t1, int upsample);
+
+/* ------------------------------------------------------------------------------------------------
+ * Banded levels: multi-type costs inside the band, banded DP, traceback.
+ * Replaces dp_core.make_sparse_costs (dp_core.pyx:165-267), dp_core.sparse_dp (:269-404),
+ * dp_utils.sparse_traceback + process_scores (dp_utils.py:89-143) and the path glue for the
+ * next finer level.
+ *
+ * Layouts (device): costs (A, T, B) fp32 — anti-diagonal major so that one DP step reads one
+ * contiguous T*B block (the reference's (T, A, B) is produced by the Python debug shim);
+ * bp (A+2, B) uint8 = index into types ++ [(0,1),(1,0)], SVX_BP_NONE for (-42,-42);
+ * csum (A+2, B) fp64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxAlignRec {   /* one alignment of the traceback                          */
+    int32_t x_end, y_end;      /* exclusive ends: x = [x_end-nx, x_end), y likewise       */
+    int32_t nx, ny;
+    double score;              /* process_scores() value                                  */
+} SvxAlignRec;
+
+typedef struct SvxBandJob {
+    const float *v0;           /* (k0, s0, dim)                                           */
+    const float *v1;           /* (k1, s1, dim)                                           */
+    const float *n0;           /* (k0, s0)                                                */
+    const float *n1;           /* (k1, s1)                                                */
+    const int32_t *ypath;      /* (a_len) search path y per anti-diagonal (x = a - y)     */
+    float *costs;              /* (a_len, ntypes, band)                                   */
+    const double *del_penalty; /* (1)                                                     */
+    uint8_t *bp;               /* (a_len+2, band)                                         */
+    double *csum;              /* (a_len+2, band)                                         */
+    SvxAlignRec *recs;         /* (rec_cap) alignments, written back-to-front             */
+    int32_t *nrecs;            /* (1) number of records: valid = recs[rec_cap-n, rec_cap) */
+    int32_t *next_ypath;       /* (next_len) or NULL at level 0                           */
+    int32_t *status_d;         /* (1)                                                     */
+    int32_t s0, s1, k0, k1;
+    int32_t a_len, band, width_over2, ntypes;
+    int32_t rec_cap;
+    int32_t t0, t1, next_len;  /* finer level sizes / path length (unused at level 0)     */
+    int8_t xo[SVX_MAX_TYPES];  /* alignment types (x,y), reference order; the DP appends  */
+    int8_t yo[SVX_MAX_TYPES];  /*   (0,1) and (1,0) itself                                */
+    int16_t amax;              /* max over types of xo+yo                                 */
+} SvxBandJob;
+SVX_API int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, int njobs, int dim, int mode,
+                     void *stream);
+SVX_API int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, int njobs, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host twins of the integer/fp64 DP logic (identical source compiled for the CPU) — they let
+ * the not-gpu tests check the cell update, traceback and path builder against the oracle.
+ * ---------------------------------------------------------------------------------------------- */
+SVX_API int svx_host_banded_dp(const SvxBandJob *job_host_pointers);
+SVX_API int svx_host_dense_dp(const SvxDenseJob *job_host_pointers);
+
+/* misc */
+SVX_API int svx_version(void);
+SVX_API const char *svx_last_error_string(void);
+SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVX_H_ */

@@ -1,0 +1,124 @@
+"""ctypes binding of ``libsvx.so`` (C ABI: ``include/svx.h``).
+
+The library is the product: there is no CPU fallback.  Importing this module on a machine
+without the built extension raises; calling a launcher without a CUDA device raises.
+
+Job descriptors are numpy structured arrays whose layout mirrors the C structs (checked against
+``svx_sizeof_job`` at load time); the launchers take the device copy and the host copy.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvx.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+SVX_COST_EXACT, SVX_COST_FAST = 0, 1
+SVX_ST_LEFT_BAND, SVX_ST_NO_BACKPTR, SVX_ST_OVERFLOW = 1, 2, 4
+SVX_BP_NONE = 255
+SVX_MAX_TYPES = 126
+
+_P = np.uint64  # device pointers travel as 64-bit integers
+
+ROWS = np.dtype([("ptr", _P), ("nrows", np.int64)], align=True)
+DOWN = np.dtype([("in", _P), ("out", _P), ("mean", _P), ("k", np.int32), ("n", np.int32)], align=True)
+NORM = np.dtype([("vecs", _P), ("other", _P), ("idx", _P), ("mbar", _P), ("norms", _P),
+                 ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32)],
+                align=True)
+SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
+                  ("scores", _P), ("del_penalty", _P),
+                  ("ne", np.int32), ("nf", np.int32), ("nsamp", np.int32)], align=True)
+DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("del_penalty", _P),
+                  ("bp", _P), ("csum", _P), ("ypath", _P), ("status_d", _P),
+                  ("s0", np.int32), ("s1", np.int32), ("t0", np.int32), ("t1", np.int32),
+                  ("upsample", np.int32), ("path_len", np.int32)], align=True)
+REC = np.dtype([("x_end", np.int32), ("y_end", np.int32), ("nx", np.int32), ("ny", np.int32),
+                ("score", np.float64)], align=True)
+BAND = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("ypath", _P), ("costs", _P),
+                 ("del_penalty", _P), ("bp", _P), ("csum", _P), ("recs", _P), ("nrecs", _P),
+                 ("next_ypath", _P), ("status_d", _P),
+                 ("s0", np.int32), ("s1", np.int32), ("k0", np.int32), ("k1", np.int32),
+                 ("a_len", np.int32), ("band", np.int32), ("width_over2", np.int32), ("ntypes", np.int32),
+                 ("rec_cap", np.int32), ("t0", np.int32), ("t1", np.int32), ("next_len", np.int32),
+                 ("xo", np.int8, (SVX_MAX_TYPES,)), ("yo", np.int8, (SVX_MAX_TYPES,)),
+                 ("amax", np.int16)], align=True)
+
+_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC]
+
+_lib = None
+
+
+class SvxError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a into libsvx.so (csrc/Makefile: nvcc -gencode
+    arch=compute_100a,code=sm_100a -lineinfo).  Cross-compiles without a GPU."""
+    out = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise SvxError("libsvx.so build failed:\n" + out.stdout[-4000:] + out.stderr[-4000:])
+    if verbose:
+        print(out.stdout[-2000:])
+    return LIB_PATH
+
+
+def lib():
+    """The loaded C ABI.  Raises if the extension has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SvxError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(the CUDA extension is the only implementation; there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    sigs = {
+        "svx_normalize_rows": [vp, vp, ci, ci, vp],
+        "svx_downsample": [vp, vp, ci, ci, vp],
+        "svx_sample_norms": [vp, vp, ci, ci, vp],
+        "svx_score_pairs": [vp, vp, ci, ci, ci, vp],
+        "svx_del_knob": [vp, vp, ci, cd, vp],
+        "svx_host_del_knob": [vp, ci, cd, vp],
+        "svx_dense_costs": [vp, vp, ci, ci, ci, vp],
+        "svx_dense_dp": [vp, vp, ci, vp],
+        "svx_path_len": [ci, ci, ci, ci, ci],
+        "svx_banded_costs": [vp, vp, ci, ci, ci, vp],
+        "svx_banded_dp": [vp, vp, ci, vp],
+        "svx_host_banded_dp": [vp],
+        "svx_host_dense_dp": [vp],
+        "svx_version": [],
+        "svx_sizeof_job": [ci],
+    }
+    for name, args in sigs.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = ci
+    L.svx_last_error_string.argtypes = []
+    L.svx_last_error_string.restype = ctypes.c_char_p
+    for i, dt in enumerate(_STRUCTS):
+        c_size = L.svx_sizeof_job(i)
+        if c_size != dt.itemsize:
+            raise SvxError(f"struct #{i} layout mismatch: C {c_size} B vs numpy {dt.itemsize} B")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_score_pairs", "svx_del_knob",
+    "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_path_len", "svx_banded_costs",
+    "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_version",
+    "svx_last_error_string", "svx_sizeof_job",
+]
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise SvxError(f"{what} failed (code {rc}): {lib().svx_last_error_string().decode()}")
+
+
+def hptr(a: np.ndarray) -> int:
+    return a.ctypes.data

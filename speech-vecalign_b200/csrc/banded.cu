@@ -1,0 +1,462 @@
+// banded.cu — fine levels (sm_100a): multi-type cosine costs inside the search band, the banded
+// anti-diagonal DP, its traceback (alignment records + scores) and the next level's search path.
+//   svx_banded_costs (dp_core.pyx:165-267 make_sparse_costs)
+//   svx_banded_dp    (dp_core.pyx:269-404 sparse_dp; dp_utils.py:89-143 sparse_traceback +
+//                     process_scores; dp_utils.py:177-275 path glue)
+#include "svx_common.cuh"
+#include "svx_dp.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Banded costs.
+//
+// One CTA owns TA consecutive anti-diagonals of one job; thread = one band cell (a, b), which
+// needs, for every alignment type (xo,yo), the dot product of overlap row xo-1 ending at segment
+// xx with overlap row yo-1 ending at yy.  Because the search path advances x or y by one per
+// anti-diagonal, the TA*B cells of a tile touch only NX + NY = TA + 2B - 1 distinct segment
+// positions: those rows (x CX/CY overlaps) are staged through shared memory in DC-float slices
+// with coalesced 16-byte loads, and every thread keeps all its type accumulators in registers,
+// adding products in increasing d (the reference order; EXACT = separate multiply and add).
+//
+//   TRI  = true : the standard type set of make_alignment_types(a) (vecalign.py:154-162), K = a-1
+//                 overlaps per side, accumulators (i,j) with i + j <= K-1, one pass.
+//   TRI  = false: any type list; passes over CX x CY blocks of (x overlap, y overlap) with a
+//                 lookup table (kx,ky) -> type index.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBC = 64;         // floats of the embedding dimension per staged slice
+constexpr int kBS = kBC + 4;    // padded row stride (68 floats = 17 x 16 B: conflict-free LDS.128)
+
+template <int CX, int CY, bool TRI, bool EXACT>
+__global__ void __launch_bounds__(384)
+k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
+{
+    extern __shared__ __align__(16) float tile[];
+    __shared__ int16_t tmap[TRI ? 1 : 64 * 64];   // (kx,ky) -> type index, generic path only
+    const SvxBandJob &job = jobs[blockIdx.y];
+    const int a0 = blockIdx.x * ta;
+    if (a0 >= job.a_len) return;
+    const int na = min(ta, job.a_len - a0);
+    const int B = job.band, w = job.width_over2, T = job.ntypes;
+    const int s0 = job.s0, s1 = job.s1;
+    const int boff_first = job.ypath[a0] - w;
+    const int boff_last = job.ypath[a0 + na - 1] - w;
+    const int ylo = boff_first, yhi = boff_last + B - 1;
+    const int xlo = a0 - boff_first - B + 1, xhi = (a0 + na - 1) - boff_last;
+    const int NX = xhi - xlo + 1, NY = yhi - ylo + 1;
+
+    const int tid = threadIdx.x;
+    const bool has_cell = tid < na * B;
+    const int la = has_cell ? tid / B : 0, b = has_cell ? tid % B : 0;
+    const int a = a0 + la;
+    const int yy = job.ypath[a] - w + b;
+    const int xx = a - yy;
+    const bool inside = has_cell && xx >= 0 && xx < s0 && yy >= 0 && yy < s1;
+    const int xr = xx - xlo, yr = yy - ylo;
+
+    int kxmax = 0, kymax = 0;     // overlaps actually referenced by the type list
+    if (!TRI) {
+        for (int i = tid; i < 64 * 64; i += blockDim.x) tmap[i] = -1;
+        __syncthreads();
+        for (int t = tid; t < T; t += blockDim.x) tmap[(job.xo[t] - 1) * 64 + (job.yo[t] - 1)] = (int16_t)t;
+        for (int t = 0; t < T; ++t) { kxmax = max(kxmax, (int)job.xo[t]); kymax = max(kymax, (int)job.yo[t]); }
+        __syncthreads();
+    } else {
+        kxmax = CX; kymax = CY;
+    }
+
+    const int slices = dim / kBC;
+    for (int kx0 = 0; kx0 < kxmax; kx0 += CX) {
+        for (int ky0 = 0; ky0 < kymax; ky0 += CY) {
+            if (TRI && (kx0 | ky0)) break;
+            float acc[CX][CY];
+#pragma unroll
+            for (int i = 0; i < CX; ++i)
+#pragma unroll
+                for (int j = 0; j < CY; ++j) acc[i][j] = 0.0f;
+
+            const int xrows = CX * NX, nrows = xrows + CY * NY;
+            for (int sl = 0; sl < slices; ++sl) {
+                const int d0 = sl * kBC;
+                __syncthreads();
+                for (int f = tid; f < nrows * (kBC / 4); f += blockDim.x) {
+                    const int row = f / (kBC / 4), c4 = f % (kBC / 4);
+                    const float *src = nullptr;
+                    if (row < xrows) {
+                        const int k = kx0 + row / NX, seg = xlo + row % NX;
+                        if (k < job.k0 && seg >= 0 && seg < s0) src = job.v0 + ((size_t)k * s0 + seg) * dim;
+                    } else {
+                        const int r2 = row - xrows;
+                        const int k = ky0 + r2 / NY, seg = ylo + r2 % NY;
+                        if (k < job.k1 && seg >= 0 && seg < s1) src = job.v1 + ((size_t)k * s1 + seg) * dim;
+                    }
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (src) v = ldg_f4(src + d0 + 4 * c4);
+                    *reinterpret_cast<float4 *>(tile + (size_t)row * kBS + 4 * c4) = v;
+                }
+                __syncthreads();
+                if (inside) {
+#pragma unroll 2
+                    for (int d = 0; d < kBC; d += 4) {
+                        float4 xv[CX], yv[CY];
+#pragma unroll
+                        for (int i = 0; i < CX; ++i)
+                            xv[i] = *reinterpret_cast<const float4 *>(tile + (size_t)(i * NX + xr) * kBS + d);
+#pragma unroll
+                        for (int j = 0; j < CY; ++j)
+                            yv[j] = *reinterpret_cast<const float4 *>(tile + (size_t)(xrows + j * NY + yr) * kBS + d);
+#pragma unroll
+                        for (int i = 0; i < CX; ++i)
+#pragma unroll
+                            for (int j = 0; j < CY; ++j) {
+                                if (TRI && i + j > CX - 1) continue;
+                                if (EXACT) {
+                                    acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(xv[i].x, yv[j].x));
+                                    acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(xv[i].y, yv[j].y));
+                                    acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(xv[i].z, yv[j].z));
+                                    acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(xv[i].w, yv[j].w));
+                                } else {
+                                    acc[i][j] = fmaf(xv[i].x, yv[j].x, acc[i][j]);
+                                    acc[i][j] = fmaf(xv[i].y, yv[j].y, acc[i][j]);
+                                    acc[i][j] = fmaf(xv[i].z, yv[j].z, acc[i][j]);
+                                    acc[i][j] = fmaf(xv[i].w, yv[j].w, acc[i][j]);
+                                }
+                            }
+                    }
+                }
+            }
+            if (has_cell) {
+                float *out = job.costs + (size_t)a * T * B + b;
+                int tri_t = 0;
+#pragma unroll
+                for (int i = 0; i < CX; ++i)
+#pragma unroll
+                    for (int j = 0; j < CY; ++j) {
+                        int t;
+                        if (TRI) {
+                            if (i + j > CX - 1) continue;
+                            t = tri_t++;            // x outer, y inner: vecalign.py:154-162 order
+                        } else {
+                            const int kx = kx0 + i, ky = ky0 + j;
+                            t = (kx < 64 && ky < 64) ? tmap[kx * 64 + ky] : -1;
+                            if (t < 0) continue;
+                        }
+                        float c = INFINITY;
+                        if (inside) {
+                            const int kx = kx0 + i, ky = ky0 + j;
+                            c = svx_band_cost(acc[i][j], kx + 1, ky + 1, job.n0[(size_t)kx * s0 + xx],
+                                              job.n1[(size_t)ky * s1 + yy]);
+                        }
+                        out[(size_t)t * B] = c;
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Banded DP: one CTA of 4 warps per job.  Warp 0 runs the anti-diagonal recurrence, lane = band
+// slot, with the last R diagonals of fp64 cumulative costs in a shared-memory ring; all warps
+// stage the next chunk of cost diagonals (contiguous T*B floats each) and band offsets into a
+// double buffer while warp 0 computes.  Backpointers are uint8 type indices in HBM; the walk and
+// the next search path follow in the same kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 32;      // anti-diagonals staged per buffer
+
+struct BandSmem {
+    double *ring;      // R * B
+    float *cost[2];    // kChunk * T * B each
+    int *boff[2];      // kChunk + R each: b_offset_out of diagonals [chunk_start - R, chunk_end)
+};
+
+struct RecWriter {
+    SvxAlignRec *recs;
+    int cap;
+    int count;
+    int lane;
+    int overflow;
+};
+
+template <class Builder>
+struct OnAlignDev {
+    RecWriter *rw;
+    Builder *pb;     // may be null
+    __host__ __device__ void operator()(int x_end, int y_end, int nx, int ny, double score)
+    {
+        if (rw->recs) {
+            if (rw->count < rw->cap) {
+                if (rw->lane == 0) {
+                    SvxAlignRec r; r.x_end = x_end; r.y_end = y_end; r.nx = nx; r.ny = ny; r.score = score;
+                    rw->recs[rw->cap - 1 - rw->count] = r;
+                }
+            } else rw->overflow = 1;
+        }
+        rw->count++;
+        if (pb) pb->step(x_end, y_end, nx, ny);
+    }
+};
+
+struct WarpEmitB {
+    int32_t *ypath;
+    int path_len;
+    int lane;
+    __host__ __device__ void operator()(long long xs, long long ys, long long xw, long long yw) const
+    {
+        const long long nn = xw + yw;
+        for (long long i = 1 + lane; i <= nn; i += 32) {
+            int x, y;
+            svx_slant_point(xs, ys, xw, yw, i, &x, &y);
+            if (x + y < path_len) ypath[x + y] = y;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int8_t sxo[SVX_MAX_TYPES + 2], syo[SVX_MAX_TYPES + 2];
+    const SvxBandJob &job = jobs[blockIdx.x];
+    const int B = job.band, T = job.ntypes, A = job.a_len, w = job.width_over2;
+    const int s0 = job.s0, s1 = job.s1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nodes_a = A + 2;
+    const int tb = T * B;
+
+    BandSmem sm;
+    sm.ring = reinterpret_cast<double *>(smem_raw);
+    sm.cost[0] = reinterpret_cast<float *>(sm.ring + (size_t)R * B);
+    sm.cost[1] = sm.cost[0] + (size_t)kChunk * tb;
+    sm.boff[0] = reinterpret_cast<int *>(sm.cost[1] + (size_t)kChunk * tb);
+    sm.boff[1] = sm.boff[0] + (kChunk + R);
+
+    for (int t = tid; t < T; t += blockDim.x) { sxo[t] = job.xo[t]; syo[t] = job.yo[t]; }
+    const double pen = *job.del_penalty;
+
+    // stage chunk c (node diagonals [c*kChunk, (c+1)*kChunk)) into buffer c & 1
+    auto stage = [&](int c, int first_thread, int nthreads) {
+        const int start = c * kChunk;
+        float *cb = sm.cost[c & 1];
+        int *bb = sm.boff[c & 1];
+        // cost diagonal of node diagonal aa is aa - 2
+        const int lo = start - 2, hi = min(start + kChunk, nodes_a) - 2;    // [lo, hi)
+        const int clo = max(lo, 0), chi = min(hi, A);
+        if (chi > clo) {
+            const float *src = job.costs + (size_t)clo * tb;
+            float *dst = cb + (size_t)(clo - lo) * tb;
+            const int n = (chi - clo) * tb;
+            for (int i = first_thread; i < n; i += nthreads) dst[i] = __ldg(src + i);
+        }
+        for (int i = first_thread; i < kChunk + R; i += nthreads) {
+            const int aa = start - R + i;
+            bb[i] = (aa >= 0 && aa < nodes_a) ? svx_boff_out(job.ypath, aa, w) : 0;
+        }
+    };
+
+    const int nchunks = (nodes_a + kChunk - 1) / kChunk;
+    stage(0, tid, blockDim.x);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        if (warp != 0) {
+            if (c + 1 < nchunks) stage(c + 1, tid - 32, blockDim.x - 32);
+        } else {
+            const float *cb = sm.cost[c & 1];
+            const int *bo = sm.boff[c & 1];
+            const int start = c * kChunk;
+            const int end = min(start + kChunk, nodes_a);
+            for (int aa = start; aa < end; ++aa) {
+                if (lane < B) {
+                    int bp;
+                    auto boff = [&](int q) { return bo[q - start + R]; };            // q in (aa-R, aa]
+                    auto csum_at = [&](int aq, int bq) { return sm.ring[(size_t)(aq & (R - 1)) * B + bq]; };
+                    auto cost_at = [&](int t) { return cb[(size_t)(aa - start) * tb + (size_t)t * B + lane]; };
+                    const double v = svx_band_node(aa, lane, s0, s1, A, B, T, sxo, syo, pen, boff, csum_at, cost_at, &bp);
+                    // ring slot aa & (R-1) held diagonal aa - R, which no type can reach any more
+                    sm.ring[(size_t)(aa & (R - 1)) * B + lane] = v;
+                    job.bp[(size_t)aa * B + lane] = (uint8_t)bp;
+                    job.csum[(size_t)aa * B + lane] = v;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+
+    // traceback + next search path (warp 0; every lane walks, lane 0 writes the records)
+    if (warp == 0) {
+        RecWriter rw{job.recs, job.rec_cap, 0, lane, 0};
+        int st;
+        if (job.next_ypath) {
+            WarpEmitB emit{job.next_ypath, job.next_len, lane};
+            SvxPathBuilder<WarpEmitB> pb(emit);
+            pb.begin(s0, s1, job.t0, job.t1, 1);
+            OnAlignDev<SvxPathBuilder<WarpEmitB>> on{&rw, &pb};
+            st = svx_band_walk(job.bp, job.csum, job.ypath, w, s0, s1, A, B, T, sxo, syo, on);
+            if (st == SVX_ST_OK) pb.finish();
+            if (lane == 0 && job.next_len > 0) job.next_ypath[0] = 0;
+        } else {
+            OnAlignDev<SvxPathBuilder<WarpEmitB>> on{&rw, nullptr};
+            st = svx_band_walk(job.bp, job.csum, job.ypath, w, s0, s1, A, B, T, sxo, syo, on);
+        }
+        if (rw.overflow) st |= SVX_ST_OVERFLOW;
+        if (lane == 0) {
+            *job.status_d = st;
+            if (job.nrecs) *job.nrecs = rw.count;
+        }
+    }
+}
+
+inline bool is_standard_types(const SvxBandJob &j, int *k_out)
+{
+    // make_alignment_types(a): x outer 1..a-1, y inner, x+y <= a  -> K = a-1, T = K(K+1)/2
+    int K = 0;
+    while (K * (K + 1) / 2 < j.ntypes) ++K;
+    if (K * (K + 1) / 2 != j.ntypes || K < 1 || K > 9) return false;
+    int t = 0;
+    for (int x = 1; x <= K; ++x)
+        for (int y = 1; x + y <= K + 1; ++y, ++t)
+            if (j.xo[t] != x || j.yo[t] != y) return false;
+    if (j.k0 < K || j.k1 < K) return false;
+    *k_out = K;
+    return true;
+}
+
+template <int CX, int CY, bool TRI>
+int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, cudaStream_t st)
+{
+    const int ta = 384 / band < 16 ? 384 / band : 16;   // <= 384 threads: up to 170 registers each
+    if (ta < 1) return -1;
+    int threads = ((ta * band + 31) / 32) * 32;
+    const int maxk = CX > CY ? CX : CY;
+    const size_t smem = (size_t)maxk * (ta + 2 * band - 1) * kBS * sizeof(float);
+    if (smem > 220 * 1024) return -1;
+    dim3 grid((max_alen + ta - 1) / ta, nj);
+    if (mode == SVX_COST_EXACT) {
+        auto kern = k_banded_costs<CX, CY, TRI, true>;
+        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta);
+    } else {
+        auto kern = k_banded_costs<CX, CY, TRI, false>;
+        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta);
+    }
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
+}  // namespace
+
+// All jobs of one call must share (band, type list); the host side groups them (level 0 jobs vs
+// coarser-level jobs of a batch differ in their type list).
+extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, int njobs, int dim, int mode,
+                                void *stream)
+{
+    SVX_REQUIRE(dim > 0 && dim % kBC == 0, SVX_ERR_UNSUPPORTED, "svx_banded_costs: dim %d must be a multiple of %d", dim, kBC);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SvxBandJob &j0 = jobs_h[0];
+    int K = 0;
+    bool standard = is_standard_types(j0, &K);
+    int max_alen = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const SvxBandJob &jb = jobs_h[j];
+        SVX_REQUIRE(jb.band == j0.band && jb.ntypes == j0.ntypes && jb.width_over2 == j0.width_over2, SVX_ERR_ARG,
+                    "svx_banded_costs: job %d differs from job 0 in band/ntypes", j);
+        SVX_REQUIRE(jb.band == 2 * jb.width_over2, SVX_ERR_ARG, "svx_banded_costs: band != 2*width_over2");
+        for (int t = 0; t < jb.ntypes; ++t) {
+            SVX_REQUIRE(jb.xo[t] == j0.xo[t] && jb.yo[t] == j0.yo[t], SVX_ERR_ARG, "svx_banded_costs: type lists differ");
+            // dp_core.pyx:204-209
+            SVX_REQUIRE(jb.xo[t] >= 1 && jb.yo[t] >= 1 && jb.xo[t] <= jb.k0 && jb.yo[t] <= jb.k1 && jb.xo[t] <= 64 && jb.yo[t] <= 64,
+                        SVX_ERR_ARG, "svx_banded_costs: type (%d,%d) needs more overlaps than provided (%d,%d)",
+                        jb.xo[t], jb.yo[t], jb.k0, jb.k1);
+        }
+        if (jb.a_len > max_alen) max_alen = jb.a_len;
+        int kk;
+        if (standard && !(is_standard_types(jb, &kk) && kk == K)) standard = false;
+    }
+    if (max_alen == 0 || j0.ntypes == 0) return SVX_OK;
+    for (int jb0 = 0; jb0 < njobs; jb0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - jb0 < SVX_MAX_GRID_Y ? njobs - jb0 : SVX_MAX_GRID_Y;
+        int rc = -1;
+        if (standard) {
+            switch (K) {
+#define CASE(KK) case KK: rc = launch_costs<KK, KK, true>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st); break;
+                CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+#undef CASE
+                default: break;
+            }
+        }
+        if (rc == -1) rc = launch_costs<4, 4, false>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st);
+        SVX_REQUIRE(rc != -1, SVX_ERR_UNSUPPORTED, "svx_banded_costs: band %d too wide for one CTA", j0.band);
+        if (rc != SVX_OK) return rc;
+    }
+    return SVX_OK;
+}
+
+static inline int ring_size(int amax)
+{
+    int r = 2;
+    while (r < amax + 1) r <<= 1;
+    return r;
+}
+
+extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, int njobs, void *stream)
+{
+    if (njobs <= 0) return SVX_OK;
+    int amax = 2, tbmax = 0, bmax = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const SvxBandJob &jb = jobs_h[j];
+        SVX_REQUIRE(jb.band >= 2 && jb.band <= 32, SVX_ERR_UNSUPPORTED, "svx_banded_dp: band %d must be in [2,32]", jb.band);
+        SVX_REQUIRE(jb.ntypes >= 0 && jb.ntypes <= SVX_MAX_TYPES - 2, SVX_ERR_ARG, "svx_banded_dp: too many types");
+        SVX_REQUIRE(jb.a_len >= 1, SVX_ERR_ARG, "svx_banded_dp: empty search path");
+        for (int t = 0; t < jb.ntypes; ++t) if (jb.xo[t] + jb.yo[t] > amax) amax = jb.xo[t] + jb.yo[t];
+        if (jb.ntypes * jb.band > tbmax) tbmax = jb.ntypes * jb.band;
+        if (jb.band > bmax) bmax = jb.band;
+    }
+    const int R = ring_size(amax);
+    const size_t smem = (size_t)R * bmax * sizeof(double) + (size_t)2 * kChunk * tbmax * sizeof(float) +
+                        (size_t)2 * (kChunk + R) * sizeof(int) + 16;
+    SVX_REQUIRE(smem <= 220 * 1024, SVX_ERR_UNSUPPORTED, "svx_banded_dp: %zu B of shared memory needed", smem);
+    if (smem > 48 * 1024)
+        SVX_CUDA_OK(cudaFuncSetAttribute(k_banded_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_banded_dp<<<njobs, 128, smem, (cudaStream_t)stream>>>(jobs_d, R);
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
+// Host twin of k_banded_dp: same node function and walk, serial loops, host pointers.
+extern "C" int svx_host_banded_dp(const SvxBandJob *job)
+{
+    SVX_REQUIRE(job && job->bp && job->csum && job->ypath && job->status_d && job->del_penalty, SVX_ERR_ARG,
+                "svx_host_banded_dp: null pointer");
+    const int B = job->band, T = job->ntypes, A = job->a_len, w = job->width_over2;
+    const double pen = *job->del_penalty;
+    for (int aa = 0; aa < A + 2; ++aa) {
+        for (int bb = 0; bb < B; ++bb) {
+            int bp;
+            auto boff = [&](int q) { return svx_boff_out(job->ypath, q, w); };
+            auto csum_at = [&](int aq, int bq) { return job->csum[(size_t)aq * B + bq]; };
+            auto cost_at = [&](int t) { return job->costs[((size_t)(aa - 2) * T + t) * B + bb]; };
+            const double v = svx_band_node(aa, bb, job->s0, job->s1, A, B, T, job->xo, job->yo, pen, boff, csum_at, cost_at, &bp);
+            job->csum[(size_t)aa * B + bb] = v;
+            job->bp[(size_t)aa * B + bb] = (uint8_t)bp;
+        }
+    }
+    RecWriter rw{job->recs, job->rec_cap, 0, 0, 0};
+    int st;
+    if (job->next_ypath) {
+        SvxSerialEmit emit{job->next_ypath, job->next_len};
+        SvxPathBuilder<SvxSerialEmit> pb(emit);
+        pb.begin(job->s0, job->s1, job->t0, job->t1, 1);
+        OnAlignDev<SvxPathBuilder<SvxSerialEmit>> on{&rw, &pb};
+        st = svx_band_walk(job->bp, job->csum, job->ypath, w, job->s0, job->s1, A, B, T, job->xo, job->yo, on);
+        if (st == SVX_ST_OK) pb.finish();
+        if (job->next_len > 0) job->next_ypath[0] = 0;
+    } else {
+        OnAlignDev<SvxPathBuilder<SvxSerialEmit>> on{&rw, nullptr};
+        st = svx_band_walk(job->bp, job->csum, job->ypath, w, job->s0, job->s1, A, B, T, job->xo, job->yo, on);
+    }
+    if (rw.overflow) st |= SVX_ST_OVERFLOW;
+    *job->status_d = st;
+    if (job->nrecs) *job->nrecs = rw.count;
+    return SVX_OK;
+}

@@ -1,0 +1,409 @@
+// prologue.cu — HBM-streaming kernels in front of the DP (sm_100a):
+//   svx_normalize_rows  (dp_utils.py:32-40   make_norm1)
+//   svx_downsample      (dp_utils.py:362-378 downsample_vectors)
+//   svx_sample_norms    (dp_utils.py:326-359 compute_norms, GEMV form)
+//   svx_score_pairs     (dp_core.pyx:143-161 score_path)
+//   svx_del_knob        (dp_utils.py:43-79   DeletionKnob, numpy >= 2 arithmetic)
+//
+// Row kernels use one warp per 4 KB embedding row: eight coalesced 16-byte loads per lane
+// (one 128-float numpy "pairwise block" per load step), the numpy pairwise-sum tree is then
+// replayed exactly through a padded, bank-conflict-free shared-memory transpose.
+#include "svx_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kRowPad = 136;  // 128-float block + 8 pad floats: (lane + 8 i) % 32 banks
+
+// ---------------------------------------------------------------------------------------------
+// numpy pairwise sum of one row's squares, bit-exact (numpy/_core/src/umath/loops_utils.h.src
+// pairwise_sum: 8 sequential accumulators per <=128-element block, balanced tree above).
+// sq: this warp's padded scratch, already holding the DIM squares.  Returns the sum in all lanes.
+// ---------------------------------------------------------------------------------------------
+template <int DIM>
+__device__ __forceinline__ float np_pairwise_from_smem(const float *sq, int lane)
+{
+    constexpr int NB = DIM / 128;            // pairwise leaf blocks
+    constexpr int NACC = NB * 8;             // leaf accumulators
+    constexpr int NPASS = (NACC + 31) / 32;
+    float pass_sum[NPASS];
+#pragma unroll
+    for (int m = 0; m < NPASS; ++m) {
+        const int q = lane + 32 * m;
+        float acc = 0.0f;
+        if (q < NACC) {
+            const float *p = sq + (q >> 3) * kRowPad + (q & 7);
+            acc = p[0];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) acc = __fadd_rn(acc, p[8 * i]);
+        }
+        // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) inside a block, then the block tree
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+        acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+        if (NB >= 2) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+        if (NB >= 4) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));
+        pass_sum[m] = acc;
+    }
+    float total;
+    if constexpr (NPASS == 1) total = pass_sum[0];
+    else if constexpr (NPASS == 2) total = __fadd_rn(pass_sum[0], pass_sum[1]);
+    else total = __fadd_rn(__fadd_rn(pass_sum[0], pass_sum[1]), __fadd_rn(pass_sum[2], pass_sum[3]));
+    return __shfl_sync(0xffffffffu, total, 0);
+}
+
+// v[s] holds elements s*128 + 4*lane .. +3 of the row.  Normalises in registers.
+template <int DIM>
+__device__ __forceinline__ void warp_unit_row(float4 (&v)[DIM / 128], float *sq, int lane)
+{
+    constexpr int NB = DIM / 128;
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+        float4 q;
+        q.x = __fmul_rn(v[s].x, v[s].x); q.y = __fmul_rn(v[s].y, v[s].y);
+        q.z = __fmul_rn(v[s].z, v[s].z); q.w = __fmul_rn(v[s].w, v[s].w);
+        *reinterpret_cast<float4 *>(sq + s * kRowPad + 4 * lane) = q;
+    }
+    __syncwarp();
+    const float total = np_pairwise_from_smem<DIM>(sq, lane);
+    __syncwarp();
+    const float den = __fadd_rn(__fsqrt_rn(total), 1e-5f);
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+        v[s].x = __fdiv_rn(v[s].x, den); v[s].y = __fdiv_rn(v[s].y, den);
+        v[s].z = __fdiv_rn(v[s].z, den); v[s].w = __fdiv_rn(v[s].w, den);
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_normalize(const SvxRows *jobs)
+{
+    constexpr int NB = DIM / 128;
+    __shared__ __align__(16) float scratch[kWarpsPerCta][NB * kRowPad];
+    const SvxRows job = jobs[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < job.nrows;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        float *p = job.ptr + row * DIM;
+        float4 v[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) v[s] = *reinterpret_cast<const float4 *>(p + s * 128 + 4 * lane);
+        warp_unit_row<DIM>(v, scratch[warp], lane);
+#pragma unroll
+        for (int s = 0; s < NB; ++s) *reinterpret_cast<float4 *>(p + s * 128 + 4 * lane) = v[s];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// downsample, pass A: out[o,j,:] = in[o,2j,:] + in[o,2j+1,:] and the per-overlap mean row.
+// np.mean(axis=0) accumulates the rows sequentially in fp32, so one thread owns one column.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pairsum_colmean(const SvxDownJob *jobs, int dim)
+{
+    const SvxDownJob job = jobs[blockIdx.y];
+    const int cblocks = dim >> 7;
+    const int o = blockIdx.x / cblocks;
+    if (o >= job.k) return;
+    const int c = (blockIdx.x % cblocks) * 128 + threadIdx.x;
+    const int m = job.n >> 1;
+    if (m == 0) return;
+    const float *src = job.in + (size_t)o * job.n * dim + c;
+    float *dst = job.out + (size_t)o * m * dim + c;
+    float acc = 0.0f;
+    int j = 0;
+    for (; j + 4 <= m; j += 4) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = __ldg(src + (size_t)(2 * j + u) * dim);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float h = __fadd_rn(a[2 * u], a[2 * u + 1]);
+            dst[(size_t)(j + u) * dim] = h;
+            acc = (j + u == 0) ? h : __fadd_rn(acc, h);
+        }
+    }
+    for (; j < m; ++j) {
+        const float h = __fadd_rn(__ldg(src + (size_t)(2 * j) * dim), __ldg(src + (size_t)(2 * j + 1) * dim));
+        dst[(size_t)j * dim] = h;
+        acc = (j == 0) ? h : __fadd_rn(acc, h);
+    }
+    job.mean[(size_t)o * dim + c] = __fdiv_rn(acc, (float)m);
+}
+
+// downsample, pass B: row -= mean row; unit-normalise.  In place on `out`.
+template <int DIM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_center_normalize(const SvxDownJob *jobs)
+{
+    constexpr int NB = DIM / 128;
+    __shared__ __align__(16) float scratch[kWarpsPerCta][NB * kRowPad];
+    const SvxDownJob job = jobs[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = job.n >> 1;
+    const int64_t nrows = (int64_t)job.k * m;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < nrows;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        const int o = (int)(row / m);
+        float *p = job.out + row * DIM;
+        const float *mu = job.mean + (size_t)o * DIM;
+        float4 v[NB];
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            const float4 h = *reinterpret_cast<const float4 *>(p + s * 128 + 4 * lane);
+            const float4 g = *reinterpret_cast<const float4 *>(mu + s * 128 + 4 * lane);
+            v[s].x = __fsub_rn(h.x, g.x); v[s].y = __fsub_rn(h.y, g.y);
+            v[s].z = __fsub_rn(h.z, g.z); v[s].w = __fsub_rn(h.w, g.w);
+        }
+        warp_unit_row<DIM>(v, scratch[warp], lane);
+#pragma unroll
+        for (int s = 0; s < NB; ++s) *reinterpret_cast<float4 *>(p + s * 128 + 4 * lane) = v[s];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample norms.  S1: mean sample vector in fp64; S2: norms = 1 - row . mbar (fp64 accumulate).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_sample_mean(const SvxNormJob *jobs, int dim)
+{
+    const SvxNormJob job = jobs[blockIdx.y];
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const int nsamp = job.ko * job.per;
+    if (nsamp <= 0 || job.no <= 0) return;
+    double acc = 0.0;
+    for (int o = 0; o < job.ko; ++o) {
+        const float *base = job.other + (size_t)o * job.no * dim + c;
+        const int32_t *ix = job.idx + (size_t)o * job.per;
+        for (int s = 0; s < job.per; ++s) acc += (double)__ldg(base + (size_t)__ldg(ix + s) * dim);
+    }
+    job.mbar[c] = acc / (double)nsamp;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) k_norms_gemv(const SvxNormJob *jobs)
+{
+    constexpr int NB = DIM / 128;
+    __shared__ double mb[DIM];
+    const SvxNormJob job = jobs[blockIdx.y];
+    const int64_t nrows = (int64_t)job.k * job.n;
+    if ((int64_t)blockIdx.x * kWarpsPerCta >= nrows) return;
+    for (int i = threadIdx.x; i < DIM; i += blockDim.x) mb[i] = job.mbar[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t row = (int64_t)blockIdx.x * kWarpsPerCta + warp; row < nrows;
+         row += (int64_t)gridDim.x * kWarpsPerCta) {
+        const float *p = job.vecs + row * DIM;
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < NB; ++s) {
+            const float4 v = ldg_f4(p + s * 128 + 4 * lane);
+            const double *q = mb + s * 128 + 4 * lane;
+            acc = fma((double)v.x, q[0], acc); acc = fma((double)v.y, q[1], acc);
+            acc = fma((double)v.z, q[2], acc); acc = fma((double)v.w, q[3], acc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) job.norms[row] = __fsub_rn(1.0f, (float)acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampled pair scores: one thread per sample, the dot product in the reference's order.
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(128) k_score_pairs(const SvxScoreJob *jobs, int dim)
+{
+    const SvxScoreJob job = jobs[blockIdx.y];
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= job.nsamp) return;
+    int xi, yi;
+    if (job.xi) { xi = job.xi[i]; yi = job.yi[i]; }
+    else { xi = i / job.nf; yi = i % job.nf; }
+    const float *a = job.e + (size_t)xi * dim;
+    const float *b = job.f + (size_t)yi * dim;
+    float dot = 0.0f;
+    for (int d = 0; d < dim; d += 8) {
+        const float4 a0 = ldg_f4(a + d), a1 = ldg_f4(a + d + 4);
+        const float4 b0 = ldg_f4(b + d), b1 = ldg_f4(b + d + 4);
+        if (EXACT) {
+            dot = __fadd_rn(dot, __fmul_rn(a0.x, b0.x)); dot = __fadd_rn(dot, __fmul_rn(a0.y, b0.y));
+            dot = __fadd_rn(dot, __fmul_rn(a0.z, b0.z)); dot = __fadd_rn(dot, __fmul_rn(a0.w, b0.w));
+            dot = __fadd_rn(dot, __fmul_rn(a1.x, b1.x)); dot = __fadd_rn(dot, __fmul_rn(a1.y, b1.y));
+            dot = __fadd_rn(dot, __fmul_rn(a1.z, b1.z)); dot = __fadd_rn(dot, __fmul_rn(a1.w, b1.w));
+        } else {
+            dot = fmaf(a0.x, b0.x, dot); dot = fmaf(a0.y, b0.y, dot);
+            dot = fmaf(a0.z, b0.z, dot); dot = fmaf(a0.w, b0.w, dot);
+            dot = fmaf(a1.x, b1.x, dot); dot = fmaf(a1.y, b1.y, dot);
+            dot = fmaf(a1.z, b1.z, dot); dot = fmaf(a1.w, b1.w, dot);
+        }
+    }
+    job.scores[i] = svx_pair_score(dot, job.norm_e[xi], job.norm_f[yi]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deletion knob: one CTA per job.  max -> shared-memory histogram (integer counts are order
+// independent) -> thread 0 replays numpy's fp64 cdf / searchsorted / interp.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_del_knob(const SvxScoreJob *jobs, double frac)
+{
+    __shared__ unsigned int hist[SVX_KNOB_BINS];
+    __shared__ float wmax[8];
+    const SvxScoreJob job = jobs[blockIdx.x];
+    const int n = job.nsamp;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, job.scores[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+    for (int i = threadIdx.x; i < SVX_KNOB_BINS; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    mx = wmax[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, wmax[w]);
+    if (mx > 0.0f) {
+        const float step = __fdiv_rn(mx, (float)SVX_KNOB_BINS);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int b = svx_knob_bin(job.scores[i], mx, step);
+            if (b >= 0) atomicAdd(&hist[b], 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *job.del_penalty = svx_knob_finish(hist, mx, frac);
+}
+
+inline int rows_grid(int64_t max_rows)
+{
+    int64_t g = (max_rows + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (g < 1) g = 1;
+    if (g > 148 * 32) g = 148 * 32;   // 32 resident CTAs of 8 warps would oversubscribe; rows loop
+    return (int)g;
+}
+
+}  // namespace
+
+#define SVX_DISPATCH_DIM(dim, CALL)            \
+    switch (dim) {                             \
+        case 128: { CALL(128); break; }        \
+        case 256: { CALL(256); break; }        \
+        case 512: { CALL(512); break; }        \
+        case 1024: { CALL(1024); break; }      \
+        default: break;                        \
+    }
+
+extern "C" int svx_normalize_rows(const SvxRows *jobs_d, const SvxRows *jobs_h, int njobs, int dim, void *stream)
+{
+    SVX_REQUIRE(svx_dim_supported(dim), SVX_ERR_UNSUPPORTED, "svx_normalize_rows: dim %d not in {128,256,512,1024}", dim);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int64_t mr = 0;
+        for (int j = 0; j < nj; ++j) mr = jobs_h[j0 + j].nrows > mr ? jobs_h[j0 + j].nrows : mr;
+        if (mr == 0) continue;
+        dim3 grid(rows_grid(mr), nj);
+#define CALL(D) k_normalize<D><<<grid, kWarpsPerCta * 32, 0, st>>>(jobs_d + j0)
+        SVX_DISPATCH_DIM(dim, CALL)
+#undef CALL
+        SVX_LAUNCH_CHECK();
+    }
+    return SVX_OK;
+}
+
+extern "C" int svx_downsample(const SvxDownJob *jobs_d, const SvxDownJob *jobs_h, int njobs, int dim, void *stream)
+{
+    SVX_REQUIRE(svx_dim_supported(dim), SVX_ERR_UNSUPPORTED, "svx_downsample: dim %d unsupported", dim);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int kmax = 0; int64_t mr = 0;
+        for (int j = 0; j < nj; ++j) {
+            const SvxDownJob &jb = jobs_h[j0 + j];
+            if (jb.k > kmax) kmax = jb.k;
+            const int64_t r = (int64_t)jb.k * (jb.n / 2);
+            if (r > mr) mr = r;
+        }
+        if (mr == 0) continue;
+        dim3 ga(kmax * (dim / 128), nj);
+        k_pairsum_colmean<<<ga, 128, 0, st>>>(jobs_d + j0, dim);
+        SVX_LAUNCH_CHECK();
+        dim3 gb(rows_grid(mr), nj);
+#define CALL(D) k_center_normalize<D><<<gb, kWarpsPerCta * 32, 0, st>>>(jobs_d + j0)
+        SVX_DISPATCH_DIM(dim, CALL)
+#undef CALL
+        SVX_LAUNCH_CHECK();
+    }
+    return SVX_OK;
+}
+
+extern "C" int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs_h, int njobs, int dim, void *stream)
+{
+    SVX_REQUIRE(svx_dim_supported(dim), SVX_ERR_UNSUPPORTED, "svx_sample_norms: dim %d unsupported", dim);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j = 0; j < njobs; ++j)
+        SVX_REQUIRE(jobs_h[j].no > 0 && jobs_h[j].ko * jobs_h[j].per > 0, SVX_ERR_ARG,
+                    "svx_sample_norms: job %d has no samples (the caller fills norms with 1.0, dp_utils.py:356-357)", j);
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int64_t mr = 0;
+        for (int j = 0; j < nj; ++j) {
+            const int64_t r = (int64_t)jobs_h[j0 + j].k * jobs_h[j0 + j].n;
+            if (r > mr) mr = r;
+        }
+        dim3 g1(dim / 128, nj);
+        k_sample_mean<<<g1, 128, 0, st>>>(jobs_d + j0, dim);
+        SVX_LAUNCH_CHECK();
+        if (mr == 0) continue;
+        dim3 g2(rows_grid(mr), nj);
+#define CALL(D) k_norms_gemv<D><<<g2, kWarpsPerCta * 32, 0, st>>>(jobs_d + j0)
+        SVX_DISPATCH_DIM(dim, CALL)
+#undef CALL
+        SVX_LAUNCH_CHECK();
+    }
+    return SVX_OK;
+}
+
+extern "C" int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, int dim, int mode,
+                               void *stream)
+{
+    SVX_REQUIRE(dim > 0 && dim % 8 == 0, SVX_ERR_UNSUPPORTED, "svx_score_pairs: dim %d must be a multiple of 8", dim);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int ms = 0;
+        for (int j = 0; j < nj; ++j) ms = jobs_h[j0 + j].nsamp > ms ? jobs_h[j0 + j].nsamp : ms;
+        if (ms == 0) continue;
+        dim3 grid((ms + 127) / 128, nj);
+        if (mode == SVX_COST_EXACT) k_score_pairs<true><<<grid, 128, 0, st>>>(jobs_d + j0, dim);
+        else k_score_pairs<false><<<grid, 128, 0, st>>>(jobs_d + j0, dim);
+        SVX_LAUNCH_CHECK();
+    }
+    return SVX_OK;
+}
+
+extern "C" int svx_del_knob(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, double frac, void *stream)
+{
+    (void)jobs_h;
+    if (njobs <= 0) return SVX_OK;
+    k_del_knob<<<njobs, 256, 0, (cudaStream_t)stream>>>(jobs_d, frac);
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
+extern "C" int svx_host_del_knob(const float *scores, int n, double frac, double *del_penalty)
+{
+    SVX_REQUIRE(scores && del_penalty && n > 0, SVX_ERR_ARG, "svx_host_del_knob: bad arguments");
+    float mx = scores[0];
+    for (int i = 1; i < n; ++i) if (scores[i] > mx) mx = scores[i];   // Python max(): first maximal element
+    unsigned int hist[SVX_KNOB_BINS];
+    for (int i = 0; i < SVX_KNOB_BINS; ++i) hist[i] = 0u;
+    if (mx > 0.0f) {
+        const float step = mx / (float)SVX_KNOB_BINS;
+        for (int i = 0; i < n; ++i) {
+            const int b = svx_knob_bin(scores[i], mx, step);
+            if (b >= 0) hist[b]++;
+        }
+    }
+    *del_penalty = svx_knob_finish(hist, mx, frac);
+    return SVX_OK;
+}

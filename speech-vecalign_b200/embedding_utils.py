@@ -1,0 +1,116 @@
+"""Input contract of the alignment path (reference: svecalign/utils/embedding_utils.py): loaders
+of the ``.embed`` files and the (K, N, D) overlap tensor ``vecs[j, i+j] = emb(segments i..i+j)``.
+
+Host-side (file formats, string keys -> row ids); the arithmetic starts at ``dp_utils.vecalign``.
+``overlap_row_table`` exposes the (K, N) row-index table so that the tensor can also be gathered
+on the device straight from the fp16/fp32 rows.
+"""
+import logging
+from typing import Dict, List, Optional, Set, Tuple
+
+import numpy as np
+
+EMBED_DIM = 1024
+PAD_LABEL = "PAD"
+logger = logging.getLogger(__name__)
+
+
+def preprocess_line(line: str) -> str:
+    line = line.strip()
+    if len(line) == 0:                       # embedding_utils.py:29-35
+        logger.warning("Encountered empty line.")
+        line = '[BLANK_LINE]'
+    return line
+
+
+def load_stopes_embeddings(path: str, mode: str = "mmap") -> np.ndarray:
+    """embedding_utils.py:38-44.  stopes writes .npy-framed files; when stopes is not installed
+    the same bytes are read with numpy (verified on the shipped example)."""
+    try:
+        from stopes.utils.embedding_utils import Embedding  # noqa
+    except ImportError:
+        return np.load(path, mmap_mode="r" if mode == "mmap" else None).astype(np.float32)
+    with Embedding(path).open_for_read(mode) as e:
+        return e.astype(np.float32)
+
+
+def load_np_embeddings(embed_file: str, fp16_embed: bool) -> np.ndarray:
+    """embedding_utils.py:47-55: raw fp16/fp32 dumps."""
+    if fp16_embed:
+        return np.fromfile(embed_file, dtype=np.float16, count=-1).astype(np.float32)
+    return np.fromfile(embed_file, dtype=np.float32, count=-1)
+
+
+def load_sent_embeddings(embed_file: str, use_stopes: bool = False, fp16_embed: bool = False,
+                         stopes_mode: str = "mmap") -> np.ndarray:
+    """embedding_utils.py:58-76 — always returns fp32 (rows, EMBED_DIM)."""
+    if use_stopes:
+        emb = load_stopes_embeddings(embed_file, mode=stopes_mode)
+    else:
+        emb = load_np_embeddings(embed_file, fp16_embed)
+        if emb.size == 0:
+            raise Exception('Got empty embedding file')
+        emb = emb.reshape(emb.shape[0] // EMBED_DIM, EMBED_DIM)
+    assert emb.dtype == np.float32, embed_file
+    return emb
+
+
+def read_in_embeddings(text_file: str, embed_file: str, use_stopes: bool = False,
+                       fp16_embed: bool = False) -> Tuple[Dict[str, int], np.ndarray]:
+    """embedding_utils.py:79-103: candidate string -> first row that carries it."""
+    sent2line: Dict[str, int] = {}
+    with open(text_file, 'rt', encoding="utf-8") as fin:
+        for i, line in enumerate(fin):
+            sent2line.setdefault(line.strip(), i)
+    return sent2line, load_sent_embeddings(embed_file, use_stopes, fp16_embed)
+
+
+def make_overlap(lines: List[str], num_overlaps: int, start_id: int,
+                 ignore_indices: Optional[Set[Tuple[int, int]]] = None, comb: str = ' ',
+                 overlap_segments: bool = False) -> List[str]:
+    """embedding_utils.py:106-132: keys of the concatenations start_id..start_id+j, PAD from an
+    ignored (start, j) onwards."""
+    out: List[str] = []
+    for j in range(start_id, min(start_id + num_overlaps, len(lines))):
+        if ignore_indices and (start_id, j) in ignore_indices:
+            out.extend([PAD_LABEL] * (min(len(lines), start_id + num_overlaps) - j))
+            break
+        if overlap_segments:
+            out.append(f"{lines[start_id].split()[0]} {lines[j].split()[1]}")
+        else:
+            out.append(comb.join(lines[start_id:j + 1]))
+    return out
+
+
+def overlap_row_table(sent2id: dict, lines: List[str], max_overlaps: int,
+                      ignore_indices: Optional[Set[Tuple[int, int]]] = None,
+                      overlap_segments: bool = False) -> np.ndarray:
+    """(K, N) int32: row of the embedding file that fills vecs[j, e], -1 for a zero row (PAD,
+    unknown key, position before the document start)."""
+    lines = [preprocess_line(x) for x in lines]
+    table = np.full((max_overlaps, len(lines)), -1, dtype=np.int32)
+    for i in range(len(lines)):
+        keys = make_overlap(lines, max_overlaps, i, ignore_indices=ignore_indices,
+                            overlap_segments=overlap_segments)
+        for j, key in enumerate(keys):
+            if key != PAD_LABEL:
+                table[j, i + j] = sent2id.get(key, -1)
+    return table
+
+
+def make_doc_embedding(sent2id: dict, line_embeddings: np.ndarray, lines: List[str], max_overlaps: int,
+                       ignore_indices: Optional[Set[Tuple[int, int]]] = None,
+                       overlap_segments: bool = False) -> np.ndarray:
+    """embedding_utils.py:135-203 -> (max_overlaps, len(lines), dim) fp32; rows with NaNs, unknown
+    keys, PAD and positions before the start stay zero."""
+    table = overlap_row_table(sent2id, lines, max_overlaps, ignore_indices, overlap_segments)
+    dim = line_embeddings.shape[1]
+    vecs = np.zeros((max_overlaps, table.shape[1], dim), dtype=np.float32)
+    hit = table >= 0
+    rows = np.asarray(line_embeddings[table[hit]], dtype=np.float32)
+    bad = np.isnan(rows).any(axis=1)
+    if bad.any():
+        logger.error("loaded %d vector(s) with nan values; reset to zero", int(bad.sum()))
+        rows[bad] = 0.0
+    vecs[hit] = rows
+    return vecs
