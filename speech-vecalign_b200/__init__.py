@@ -11,9 +11,9 @@ package at the repo root) or via ``importlib.import_module("speech-vecalign_b200
 All numerics live in ``libsvx.so`` (csrc/, C ABI in include/svx.h); without it, or without a CUDA
 device, calls raise — there is no CPU fallback.
 """
-from . import capi  # noqa: F401
-from .dp_utils import vecalign, vecalign_batch  # noqa: F401
+from . import capi, dp_core, dp_utils, vecalign  # noqa: F401  (same module names as svecalign.vecalign.*)
+from .dp_utils import vecalign_batch  # noqa: F401
 from .vecalign import align, make_alignment_types, make_many_to_one_alignment_types, print_alignments  # noqa: F401
 
-__all__ = ["vecalign", "vecalign_batch", "align", "make_alignment_types",
-           "make_many_to_one_alignment_types", "print_alignments", "capi"]
+__all__ = ["capi", "dp_core", "dp_utils", "vecalign", "vecalign_batch", "align", "make_alignment_types",
+           "make_many_to_one_alignment_types", "print_alignments"]

@@ -161,7 +161,7 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
 // double buffer while warp 0 computes.  Backpointers are uint8 type indices in HBM; the walk and
 // the next search path follow in the same kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 32;      // anti-diagonals staged per buffer
+constexpr int kMaxChunk = 32;   // anti-diagonals staged per buffer (fewer when T*B is large)
 
 struct BandSmem {
     double *ring;      // R * B
@@ -211,7 +211,7 @@ struct WarpEmitB {
     }
 };
 
-__global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R)
+__global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R, int kChunk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int8_t sxo[SVX_MAX_TYPES + 2], syo[SVX_MAX_TYPES + 2];
@@ -413,12 +413,14 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
         if (jb.band > bmax) bmax = jb.band;
     }
     const int R = ring_size(amax);
-    const size_t smem = (size_t)R * bmax * sizeof(double) + (size_t)2 * kChunk * tbmax * sizeof(float) +
-                        (size_t)2 * (kChunk + R) * sizeof(int) + 16;
+    int chunk = tbmax > 0 ? (int)((96 * 1024) / ((size_t)2 * tbmax * sizeof(float))) : kMaxChunk;
+    chunk = chunk > kMaxChunk ? kMaxChunk : (chunk < 2 ? 2 : chunk);
+    const size_t smem = (size_t)R * bmax * sizeof(double) + (size_t)2 * chunk * tbmax * sizeof(float) +
+                        (size_t)2 * (chunk + R) * sizeof(int) + 16;
     SVX_REQUIRE(smem <= 220 * 1024, SVX_ERR_UNSUPPORTED, "svx_banded_dp: %zu B of shared memory needed", smem);
     if (smem > 48 * 1024)
         SVX_CUDA_OK(cudaFuncSetAttribute(k_banded_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_banded_dp<<<njobs, 128, smem, (cudaStream_t)stream>>>(jobs_d, R);
+    k_banded_dp<<<njobs, 128, smem, (cudaStream_t)stream>>>(jobs_d, R, chunk);
     SVX_LAUNCH_CHECK();
     return SVX_OK;
 }
