@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200 alignment path on BASELINE.json's workloads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5] [--pairs P]
+    python bench.py --impl reference ...       # the reference's CPU implementation, all host cores
+
+A step = one pass of the hot path (normalise -> downsample -> norms -> knob -> dense level ->
+banded levels -> traceback) over one batch of synthetic document pairs.  Default workload =
+BASELINE.json configs[1]: 2000 x 2000 segments, dim 1024, max overlap 4 (K=4, a=5), as a batch
+of --pairs independent pairs per GPU (weak scaling: every rank aligns its own batch; pairs are
+independent, no data-path collective — SURVEY.md §8e).
+
+Printed (rank 0, ONE JSON line): value = whole-job aligned pairs/s with the embeddings already
+in HBM (CUDA events, max over ranks); e2e = the same through the public API
+(speech_vecalign_b200.vecalign_batch) from pinned HOST tensors, H2D and the D2H of the packed
+results inside the timed region; roofline of the dominant kernel; cpu_baseline = the reference's
+CPU path (oracle/_ref core when present, else the oracle port) on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (description, a, fixed (n0,n1) or None, default pairs per GPU)
+    "cfg2": ("BASELINE configs[1]: synthetic pairs 2000x2000 segments, dim 1024, max overlap 4 (a=5)", 5, (2000, 2000), 64),
+    "cfg3": ("BASELINE configs[2]: synthetic long-session pairs 20000x20000, dim 1024, a=5, search_buffer_size=5", 5, (20000, 20000), 4),
+    "cfg4": ("BASELINE configs[3]: synthetic doc pairs with 200-800 segments each, a=6, length-bucketed", 6, None, 1024),
+    "cfg5": ("BASELINE configs[4]: synthetic pairs 5000x5000, dim 1024, alignment_max_size=8", 8, (5000, 5000), 16),
+}
+DIM = 1024
+PARAMS = dict(del_percentile_frac=0.2, search_buffer_size=5, max_size_full_dp=300, costs_sample_size=20000,
+              num_samps_for_norm=100)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="document pairs per GPU per step (0 = workload default)")
+    ap.add_argument("--cost-mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 3)")
+    return ap.parse_args()
+
+
+def workload_sizes(name, pairs, rank):
+    from speech_vecalign_b200 import synth
+    _, a, fixed, _ = WORKLOADS[name]
+    if fixed is not None:
+        return np.full(pairs, fixed[0], dtype=np.int64), np.full(pairs, fixed[1], dtype=np.int64), a
+    n0, n1 = synth.batch_sizes(pairs, seed=1234 + rank)
+    return n0, n1, a
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (no CUDA anywhere on this path)
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(name, a, n0, n1, seed0, counter):
+    from threadpoolctl import threadpool_limits
+    from oracle import ref_loader, vecalign_oracle as vo
+    from speech_vecalign_b200 import synth
+    with counter.get_lock():
+        wid = counter.value
+        counter.value += 1
+    _W["limits"] = threadpool_limits(1)
+    core = ref_loader.ref_core()
+    _W["core"], _W["kind"] = (core, "reference") if core is not None else (None, "port")
+    _W["vo"] = vo
+    i = wid % len(n0)
+    k = a - 1
+    _W["pair"] = synth.synth_pair(int(n0[i]), int(n1[i]), k, dim=DIM, seed=seed0 + wid)
+    _W["args"] = (vo.alignment_types(a), PARAMS["del_percentile_frac"], math.ceil(k / 2) + PARAMS["search_buffer_size"],
+                  PARAMS["max_size_full_dp"], PARAMS["costs_sample_size"], PARAMS["num_samps_for_norm"])
+    _W["a"] = a
+
+
+def _cpu_worker_step(step):
+    vo = _W["vo"]
+    v0, v1 = _W["pair"]
+    np.random.seed(step)
+    t = time.perf_counter()
+    st = vo.vecalign(v0.copy(), v1.copy(), *_W["args"], core=_W["core"])
+    dt = time.perf_counter() - t
+    w = _W["args"][2]
+    return dt, vo.dp_cells(v0.shape[1], v1.shape[1], w, PARAMS["max_size_full_dp"]), len(st[0]["final_alignments"]), _W["kind"]
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path on all host cores: one worker process per
+    core (the reference itself is a serial loop, seg_align/align.py:206; pairs are independent, so
+    this is its fair multi-core form), OpenBLAS pinned to one thread per worker.  One step = every
+    worker aligns one pair of the workload."""
+
+    def __init__(self, name, nproc=None):
+        import multiprocessing as mp
+        from oracle import core as ocore
+        ocore.build()
+        self.nproc = nproc or len(os.sched_getaffinity(0))
+        _, a, _, _ = WORKLOADS[name]
+        n0, n1, a = workload_sizes(name, max(self.nproc, 8), 0)
+        ctx = mp.get_context("fork")
+        counter = ctx.Value("i", 0)
+        self.pool = ctx.Pool(self.nproc, initializer=_cpu_worker_init, initargs=(name, a, n0, n1, 777, counter))
+        self.name = name
+
+    def step(self, i):
+        t = time.perf_counter()
+        res = self.pool.map(_cpu_worker_step, [i] * self.nproc, chunksize=1)
+        wall = time.perf_counter() - t
+        return wall, sum(r[1] for r in res), res[0][3], sum(r[0] for r in res) / len(res)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    desc, a, _, _ = WORKLOADS[args.workload]
+    ref = CpuReference(args.workload)
+    for i in range(args.warmup):
+        ref.step(i)
+    t_tot, cells, kind, per_pair = 0.0, 0, "port", 0.0
+    for i in range(args.steps):
+        w, c, kind, pp = ref.step(args.warmup + i)
+        t_tot += w
+        cells += c
+        per_pair += pp
+    ref.close()
+    value = ref.nproc * args.steps / t_tot
+    sample = f"{ref.nproc} worker processes x 1 pair of the workload per step ({args.steps} timed steps), OpenBLAS 1 thread/worker; " \
+             f"mean single-core time per pair {per_pair / args.steps:.2f} s"
+    line = {
+        "impl": "reference", "metric": "aligned doc pairs/sec (DP cells/sec alongside)", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "pairs_per_step": ref.nproc, "alignment_max_size": a, **PARAMS},
+        "dp_cells_per_sec": cells / t_tot,
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": ref.nproc, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import speech_vecalign_b200 as svb
+    from speech_vecalign_b200 import capi, synth
+    from speech_vecalign_b200.engine import BatchRun
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = capi.lib()
+
+    desc, a, _, dflt_pairs = WORKLOADS[args.workload]
+    pairs = args.pairs or dflt_pairs
+    n0, n1, a = workload_sizes(args.workload, pairs, rank)
+    k = a - 1
+    types = svb.make_alignment_types(a)
+    w = math.ceil(k / 2) + PARAMS["search_buffer_size"]
+    mode = capi.SVX_COST_EXACT if args.cost_mode == "exact" else capi.SVX_COST_FAST
+
+    # ---- synthetic inputs born in HBM: a pristine copy and the working copy the path mutates ----
+    off0 = np.concatenate([[0], np.cumsum(k * (n0 + n1) * DIM)]).astype(np.int64)
+    total = int(off0[-1])
+    pristine = torch.empty(total, dtype=torch.float32, device=dev)
+    work = torch.empty_like(pristine)
+
+    def views(buf):
+        out = []
+        for p in range(pairs):
+            b = int(off0[p])
+            m0 = k * int(n0[p]) * DIM
+            out.append((buf[b:b + m0].view(k, int(n0[p]), DIM), buf[b + m0:int(off0[p + 1])].view(k, int(n1[p]), DIM)))
+        return out
+
+    pv, wv = views(pristine), views(work)
+    for p in range(pairs):
+        synth.synth_pair_torch(int(n0[p]), int(n1[p]), k, dim=DIM, seed=100000 * rank + p, device=dev,
+                               out0=pv[p][0], out1=pv[p][1])
+    torch.cuda.synchronize()
+
+    np.random.seed(4242 + rank)
+    run = BatchRun([t0.data_ptr() for t0, _ in wv], [t1.data_ptr() for _, t1 in wv], n0, n1, k, k, DIM, types,
+                   PARAMS["del_percentile_frac"], w, PARAMS["max_size_full_dp"], PARAMS["costs_sample_size"],
+                   PARAMS["num_samps_for_norm"], dev, cost_mode=mode)
+    cells = run.dp_cells()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(timing):
+        work.copy_(pristine)                       # untimed: the path normalises its input in place
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run.run(timing=timing)
+        e1.record()
+        return e0, e1
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.svx_launch_count(1)
+    t_wall = time.perf_counter()
+    step_ms, ktimes = [], {}
+    for _ in range(args.steps):
+        e0, e1 = one_step(True)
+        kt = run.kernel_times()                    # synchronises
+        step_ms.append(e0.elapsed_time(e1))
+        for nm, ms in kt.items():
+            ktimes[nm] = ktimes.get(nm, 0.0) + ms
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = int(lib.svx_launch_count(0))
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    res = run.results()
+    n_align = sum(r["nrecs"] for r in res)
+    bad = sum(1 for r in res if r["status"])
+
+    # ---- e2e: public API, pinned host tensors in, packed records out -----------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(total, dtype=torch.float32, pin_memory=True)
+        host.copy_(pristine)
+        hv = views(host)
+        e2e_steps = args.e2e_steps or min(args.steps, 3)
+        kw = dict(final_alignment_types=types, del_percentile_frac=PARAMS["del_percentile_frac"], width_over2=w,
+                  max_size_full_dp=PARAMS["max_size_full_dp"], costs_sample_size=PARAMS["costs_sample_size"],
+                  num_samps_for_norm=PARAMS["num_samps_for_norm"], cost_mode=args.cost_mode, output="records")
+        np.random.seed(4242 + rank)
+        out = svb.vecalign_batch(hv, **kw)         # warm-up (allocator, page-locking paths)
+        d2h = sum(o["recs"].nbytes + 8 * len(o["del_penalty"]) + 8 for o in out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            out = svb.vecalign_batch(hv, **kw)
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * pairs * e2e_steps / dt, "unit": "pairs/s",
+               "h2d_bytes_per_step": int(total * 4 + run.host_init_bytes), "d2h_bytes_per_step": int(d2h),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "api": "speech_vecalign_b200.vecalign_batch(pinned host tensors, output='records')"}
+        del host
+
+    if world > 1:
+        cnt = torch.tensor([n_align, bad], device=dev, dtype=torch.int64)
+        dist.all_reduce(cnt)                        # the only exchange: result counts for the report
+        n_align, bad = int(cnt[0]), int(cnt[1])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
+        (6650.0, "fallback (B200_PROFILING.md)")
+    alg = run.algorithmic_bytes()
+    dom = max(ktimes, key=ktimes.get)
+    dom_ms = ktimes[dom] / args.steps
+    achieved = alg.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg.get(dom, 0), "ms_per_launch": dom_ms,
+                "share_of_step": ktimes[dom] / max(sum(ktimes.values()), 1e-9)}
+    kernels = {nm: {"ms_per_step": ms / args.steps, "GBps": (alg.get(nm, 0) / (ms / args.steps * 1e-3) / 1e9) if ms > 0 else None}
+               for nm, ms in sorted(ktimes.items(), key=lambda kv: -kv[1])}
+
+    # ---- parity spot check against the oracle (outside every timed region) -----------------------
+    parity = None
+    try:
+        from oracle import vecalign_oracle as vo
+        v0 = pv[0][0].cpu().numpy()
+        v1 = pv[0][1].cpu().numpy()
+        np.random.seed(4242)
+        ref = vo.vecalign(v0, v1, types, PARAMS["del_percentile_frac"], w, PARAMS["max_size_full_dp"],
+                          PARAMS["costs_sample_size"], PARAMS["num_samps_for_norm"], fast_host=True)
+        from speech_vecalign_b200.engine import records_to_alignments
+        al, sc = records_to_alignments(res[0]["recs"])
+        parity = {"pair0_identical_alignments": al == [(list(x), list(y)) for x, y in ref[0]["final_alignments"]],
+                  "pair0_max_score_diff": float(np.max(np.abs(sc - ref[0]["alignment_scores"]))) if len(sc) == len(ref[0]["alignment_scores"]) else None}
+    except Exception as e:  # the checker is optional here
+        parity = {"error": repr(e)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ref = CpuReference(args.workload)
+            ref.step(0)
+            wall, c, kind, pp = ref.step(1)
+            ref.close()
+            cpu = {"value": ref.nproc / wall, "unit": "pairs/s", "cores": ref.nproc, "kind": kind,
+                   "sample": f"{ref.nproc} worker processes x 1 pair of the workload (1 warm-up + 1 timed round), "
+                             f"OpenBLAS 1 thread/worker; single-core {pp:.2f} s/pair",
+                   "dp_cells_per_sec": c / wall}
+        except Exception as e:
+            cpu = {"error": repr(e)}
+
+    value = world * pairs * args.steps / (total_ms * 1e-3)
+    line = {
+        "metric": "aligned doc pairs/sec (DP cells/sec alongside)", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "pairs_per_gpu_per_step": pairs, "alignment_max_size": a, "dim": DIM,
+                   "cost_mode": args.cost_mode, "l2": f"inputs {total * 4 / 2**30:.2f} GiB per step > 126 MB L2 (restored from a pristine copy before every step)",
+                   **PARAMS},
+        "dp_cells_per_sec": world * cells * args.steps / (total_ms * 1e-3),
+        "alignments_per_step": n_align, "pairs_with_device_error": bad,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_s_timed_loop": t_wall,
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.gpus > 1 and "RANK" not in os.environ and args.impl == "ours":
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -209,6 +209,7 @@ SVX_API int svx_host_dense_dp(const SvxDenseJob *job_host_pointers);
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);
+SVX_API long long svx_launch_count(int reset); /* kernels launched since the last reset */
 SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec */
 
 #ifdef __cplusplus

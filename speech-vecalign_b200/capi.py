@@ -97,6 +97,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = ci
+    L.svx_launch_count.argtypes = [ci]
+    L.svx_launch_count.restype = ctypes.c_longlong
     L.svx_last_error_string.argtypes = []
     L.svx_last_error_string.restype = ctypes.c_char_p
     for i, dt in enumerate(_STRUCTS):
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_score_pairs", "svx_del_knob",
     "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_path_len", "svx_banded_costs",
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_version",
-    "svx_last_error_string", "svx_sizeof_job",
+    "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
 ]
 
 

@@ -13,6 +13,17 @@ void svx_set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void svx_count_launch(void) { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
+// number of kernels launched by this library since the last reset (bench.py's gpu_launches)
+extern "C" long long svx_launch_count(int reset)
+{
+    long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_launches, 0, __ATOMIC_RELAXED);
+    return v;
+}
+
 extern "C" int svx_version(void) { return SVX_VERSION; }
 extern "C" const char *svx_last_error_string(void) { return g_err; }
 extern "C" int svx_sizeof_job(int which)

@@ -6,6 +6,7 @@
 #include "svx_math.h"
 
 void svx_set_error(const char *fmt, ...);
+void svx_count_launch(void);
 
 #define SVX_CUDA_OK(expr)                                                                      \
     do {                                                                                       \
@@ -31,6 +32,7 @@ void svx_set_error(const char *fmt, ...);
             svx_set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
             return SVX_ERR_CUDA;                                                               \
         }                                                                                      \
+        svx_count_launch();                                                                    \
     } while (0)
 
 static inline bool svx_dim_supported(int dim)

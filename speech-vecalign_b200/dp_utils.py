@@ -53,12 +53,16 @@ def _to_device(v, dev):
 
 def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                    costs_sample_size, num_samps_for_norm, cost_mode="exact", debug=False, writeback=False,
-                   norms0=None, norms1=None, sync=True):
+                   norms0=None, norms1=None, sync=True, output="stack", seeds=None):
     """Align many document pairs in one pass over the GPU.
 
     pairs: sequence of (vecs0, vecs1), each (K, N, D) fp32 numpy array or torch tensor (host or
     device).  np.random draws are made pair by pair in input order, i.e. exactly as a serial loop of
-    the reference would consume the stream.  Returns one reference-style ``stack`` dict per pair.
+    the reference would consume the stream.  Returns one reference-style ``stack`` dict per pair, or
+    with output="records" the packed device records per pair ({'recs': SvxAlignRec array in path
+    order, 'del_penalty': [per level], 'nrecs', 'status'}) without building Python lists.
+    seeds: optional per-pair np.random seeds (np.random.seed(seeds[p]) before pair p's draws), which
+    makes every pair's result independent of batch order and of the multi-GPU partition.
     """
     if width_over2 < 3:
         logger.warning('width_over2 was set to %d, which does not make sense. increasing to 3.', width_over2)
@@ -89,16 +93,19 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
                    [t0.shape[1] for t0, _ in dv], [t1.shape[1] for _, t1 in dv],
                    k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                    costs_sample_size, num_samps_for_norm, dev, cost_mode=_MODES[cost_mode],
-                   norms0=norms0, norms1=norms1, keep_dense_csum=debug)
+                   norms0=norms0, norms1=norms1, keep_dense_csum=debug, seeds=seeds)
     run.run()
     if not sync:
         return run
     res = run.results()
-    stacks = []
     for p, r in enumerate(res):
         if r["status"]:
             # the reference fails here with IndexError / 'traceback bug' (dp_utils.py:123-124)
             raise Exception('traceback bug (device status %d for pair %d)' % (r["status"], p))
+    if output == "records":
+        return res
+    stacks = []
+    for p, r in enumerate(res):
         al, sc = records_to_alignments(r["recs"])
         st = {0: {"final_alignments": al, "alignment_scores": sc, "del_penalty": np.float64(r["del_penalty"][0])}}
         for lvl in range(1, len(r["del_penalty"])):

@@ -71,7 +71,7 @@ class _Arena:
 
 
 def draw_samples(rec_s0, rec_s1, pair_first, pair_nlev, k0, k1, num_samps_for_norm, costs_sample_size,
-                 skip_norm0, skip_norm1):
+                 skip_norm0, skip_norm1, seeds=None):
     """Replays the reference's np.random consumption for every pair, in input order
     (SURVEY.md §8a a14): per pair, for each depth ascending the n0 draws (K1 calls over range(size1))
     then the n1 draws (K0 calls over range(size0)); then for each depth ascending the knob draws
@@ -85,6 +85,8 @@ def draw_samples(rec_s0, rec_s1, pair_first, pair_nlev, k0, k1, num_samps_for_no
     knob = [None] * nrec
     for p in range(pair_first.shape[0]):
         first, nlev = int(pair_first[p]), int(pair_nlev[p])
+        if seeds is not None:                     # per-pair stream: independent of batch order / sharding
+            np.random.seed(int(seeds[p]))
         for r in range(first, first + nlev):
             a, b = int(rec_s0[r]), int(rec_s1[r])
             lvl0 = r == first
@@ -122,7 +124,7 @@ class BatchRun:
 
     def __init__(self, vec_ptrs0, vec_ptrs1, n0, n1, k0, k1, dim, alignment_types, del_percentile_frac,
                  width_over2, max_size_full_dp, costs_sample_size, num_samps_for_norm, device,
-                 cost_mode=capi.SVX_COST_EXACT, norms0=None, norms1=None, keep_dense_csum=False):
+                 cost_mode=capi.SVX_COST_EXACT, norms0=None, norms1=None, keep_dense_csum=False, seeds=None):
         self.P = P = len(n0)
         self.dev = device
         self.dim = dim
@@ -173,7 +175,7 @@ class BatchRun:
         # ---- host RNG draws (reference order) -------------------------------------------------
         self.idx0, self.idx1, self.knob, per0, per1 = draw_samples(
             rs0, rs1, self.first, self.nlev, self.k0, self.k1, int(num_samps_for_norm), self.sample_size,
-            norms0 is not None, norms1 is not None)
+            norms0 is not None, norms1 is not None, seeds=seeds)
         self.per0, self.per1 = per0, per1
         nsamp = np.zeros(R, dtype=np.int64)
         for r in range(R):
@@ -200,6 +202,7 @@ class BatchRun:
         self._jobs_off = int(o["jobs"][0])
         self._jobs_cap = jobs_bytes
         host_end = ar.top
+        self.host_init_bytes = host_end
         # device-only region
         o["norms0"] = ar.take(self.k0 * rs0 * 4)
         o["norms1"] = ar.take(self.k1 * rs1 * 4)
@@ -386,10 +389,34 @@ class BatchRun:
         if arr.shape[0] == 0:
             return
         stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self._events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            capi.check(fn(dptr, capi.hptr(arr), arr.shape[0], *extra, stream), name)
+            e1.record()
+            self._events.append((name if not isinstance(key, tuple) or key[0] != "band" else
+                                 name + ("_level0" if self._band_is_l0(key) else "_coarse"), e0, e1))
+            return
         capi.check(fn(dptr, capi.hptr(arr), arr.shape[0], *extra, stream), name)
 
-    def run(self):
+    def _band_is_l0(self, key):
+        return bool(self._job_views[key][1]["ntypes"][0] == len(self.types) and
+                    self._job_views[key][1]["next_ypath"][0] == 0)
+
+    def kernel_times(self):
+        """Per-launcher device time (ms) of the last run(timing=True), summed by launcher name;
+        CUDA events on the launching stream.  Synchronises."""
+        torch.cuda.synchronize(self.dev)
+        out = {}
+        for name, e0, e1 in self._events or []:
+            out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    _events = None
+
+    def run(self, timing=False):
         """Enqueue the whole batch on the current stream (asynchronous)."""
+        self._events = [] if timing else None
         L = capi.lib()
         D, mode = self.dim, self.cost_mode
         self._call(L.svx_normalize_rows, "svx_normalize_rows", "rows", D)
@@ -407,6 +434,37 @@ class BatchRun:
                 self._call(L.svx_banded_dp, "svx_banded_dp", ("band", s, g))
 
     # ------------------------------------------------------------------------------------------
+    def algorithmic_bytes(self):
+        """Compulsory HBM bytes per launcher for this batch (SURVEY.md §8d formulae):
+        every needed embedding row read once, every output written once."""
+        D, K0, K1, B = self.dim, self.k0, self.k1, self.band
+        s0, s1, A, T = self.rs0, self.rs1, self.A, self.T
+        l0 = self.rec_level == 0
+        top = self.rec_level == self.depth[self.rec_pair]
+        band_l0, band_co = self.banded & l0, self.banded & ~l0
+        nj = self.norm_jobs
+        out = {
+            "svx_normalize_rows": 2 * 4 * D * int(K0 * s0[l0].sum() + K1 * s1[l0].sum()),
+            "svx_downsample": 4 * D * int((K0 * (s0[~top] + 3 * (s0[~top] // 2)) + K1 * (s1[~top] + 3 * (s1[~top] // 2))).sum()),
+            "svx_sample_norms": int((nj["k"].astype(np.int64) * nj["n"] * (D * 4 + 4) +
+                                     nj["ko"].astype(np.int64) * nj["per"] * D * 4).sum()),
+            "svx_score_pairs": int((self.nsamp * (2 * D * 4 + 4)).sum()),
+            "svx_del_knob": int((self.nsamp * 8).sum()),
+            "svx_dense_costs": int(((s0[top] + s1[top]) * D * 4 + s0[top] * s1[top] * 4).sum()),
+            "svx_dense_dp": int(((s0[top] + 1) * (s1[top] + 1) * 5).sum()),
+            "svx_banded_costs_level0": int((K0 * s0[band_l0] * D * 4 + K1 * s1[band_l0] * D * 4 + 4 * T[band_l0] * A[band_l0] * B).sum()),
+            "svx_banded_costs_coarse": int(((s0[band_co] + s1[band_co]) * D * 4 + 4 * A[band_co] * B).sum()),
+            "svx_banded_dp_level0": int(((A[band_l0] + 2) * B * (4 * T[band_l0] + 9)).sum()),
+            "svx_banded_dp_coarse": int(((A[band_co] + 2) * B * (4 + 9)).sum()),
+        }
+        return out
+
+    def dp_cells(self):
+        """DP cells of the batch: banded nodes (A+2)*B per banded level plus the
+        (s0+1)(s1+1) dense nodes of the coarsest level."""
+        top = self.rec_level == self.depth[self.rec_pair]
+        return int(((self.A[self.banded] + 2) * self.band).sum() + ((self.rs0[top] + 1) * (self.rs1[top] + 1)).sum())
+
     def results(self):
         """Device -> host read of the level-0 alignment records, scores, penalties and status.
         Returns a list (one per pair) of dicts with 'recs' (structured array, forward order),
