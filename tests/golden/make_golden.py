@@ -75,12 +75,13 @@ def example():
         k = a - 1
         v0 = load("en", f"{dst}/ignore.src.txt", k)
         v1 = load("de", f"{dst}/ignore.tgt.txt", k)
+        chk = (float(np.abs(v0).sum()), float(np.abs(v1).sum()))   # before the in-place normalisation
         np.random.seed(0)
         st = du.vecalign(v0, v1, make_alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
         out[f"a{a}"] = {"alignments": jsonable_alignments(st[0]["final_alignments"]),
                         "scores": [float(s) for s in st[0]["alignment_scores"]],
                         "del_penalty": float(st[0]["del_penalty"]), "rng_seed": 0,
-                        "vecs0_checksum": float(np.abs(v0).sum()), "vecs1_checksum": float(np.abs(v1).sum())}
+                        "vecs0_checksum": chk[0], "vecs1_checksum": chk[1]}
     json.dump(out, open(os.path.join(HERE, "example_reference.json"), "w"))
 
 
@@ -142,10 +143,11 @@ def e2e():
     for n0, n1, a, seed, rseed in E2E_CASES:
         k = a - 1
         v0, v1 = synth.synth_pair(n0, n1, k, seed=seed)
+        chk = [float(np.abs(v0).sum()), float(np.abs(v1).sum())]      # before the in-place normalisation
         np.random.seed(rseed)
         st = du.vecalign(v0, v1, make_alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
         cases.append({"n0": n0, "n1": n1, "a": a, "seed": seed, "rng_seed": rseed,
-                      "input_checksum": [float(np.abs(v0).sum()), float(np.abs(v1).sum())],
+                      "input_checksum": chk,
                       "alignments": jsonable_alignments(st[0]["final_alignments"]),
                       "scores": [float(s) for s in st[0]["alignment_scores"]],
                       "del_penalty": [float(st[d]["del_penalty"]) for d in sorted(st)]})

@@ -1,0 +1,240 @@
+"""CPU: the C-ABI library loads and exports everything include/svx.h declares; the host twins of
+the DP kernels (identical source, compiled for the CPU) reproduce the reference's known answers;
+the batch planner replays the reference's RNG stream; the product refuses to run without CUDA.
+No compute call touches a GPU here."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, same_alignments
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "functions.npz"))
+
+
+def test_library_exports_every_declared_symbol(svb):
+    hdr = open(os.path.join(ROOT, "include", "svx.h")).read()
+    declared = re.findall(r"SVX_API\s+[\w\s\*]+?\b(svx_\w+)\s*\(", hdr)
+    assert len(declared) >= 17
+    L = ctypes.CDLL(svb.capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/svx.h but not exported by libsvx.so"
+    assert sorted(declared) == sorted(svb.capi.EXPORTED_SYMBOLS)
+    assert svb.capi.lib().svx_version() == 100
+
+
+def test_struct_layouts_match(svb):
+    L = svb.capi.lib()
+    for i, dt in enumerate([svb.capi.ROWS, svb.capi.DOWN, svb.capi.NORM, svb.capi.SCORE, svb.capi.DENSE,
+                            svb.capi.BAND, svb.capi.REC]):
+        assert L.svx_sizeof_job(i) == dt.itemsize
+
+
+def test_no_cpu_fallback(svb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    v = np.zeros((2, 5, 1024), np.float32)
+    with pytest.raises(svb.capi.SvxError, match="no CUDA device"):
+        svb.dp_utils.vecalign(v, v.copy(), [(1, 1)], 0.2, 7, 300, 20000, 100)
+    with pytest.raises(svb.capi.SvxError, match="no CUDA device"):
+        svb.dp_core.make_norm1(v)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "speech-vecalign_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src, f
+
+
+# ------------------------------------------------------------------------------------------------
+def test_host_del_knob_bit_exact(svb, gold):
+    L = svb.capi.lib()
+    sc = np.ascontiguousarray(gold["score_out"])
+    for frac, want in zip(gold["knob_fracs"], gold["knob_pens"]):
+        out = np.zeros(1, np.float64)
+        assert L.svx_host_del_knob(sc.ctypes.data, sc.shape[0], float(frac), out.ctypes.data) == 0
+        assert out[0] == want, (frac, out[0], want)
+
+
+@pytest.mark.parametrize("seed,n", [(0, 20000), (1, 777), (2, 3), (3, 1)])
+def test_host_del_knob_random(svb, oracle, seed, n):
+    rng = np.random.default_rng(seed)
+    sc = np.abs(rng.normal(0.9, 0.3, n)).astype(np.float32)
+    knob = oracle.PercentileKnob(sc, 0, max(sc))
+    for frac in (0.0, 0.02, 0.2, 0.33, 0.8, 1.0):
+        out = np.zeros(1, np.float64)
+        svb.capi.lib().svx_host_del_knob(sc.ctypes.data, n, frac, out.ctypes.data)
+        assert out[0] == knob.percentile_frac_to_del_penalty(frac)
+
+
+def _dense_job(svb, costs, pen, t0, t1, ups):
+    s0, s1 = costs.shape
+    keep = {}
+    keep["costs"] = np.ascontiguousarray(costs, dtype=np.float32)
+    keep["pen"] = np.array([pen], np.float64)
+    keep["bp"] = np.zeros((s0 + 1, s1 + 1), np.uint8)
+    keep["csum"] = np.zeros((s0 + 1, s1 + 1), np.float64)
+    plen = svb.capi.lib().svx_path_len(s0, s1, t0, t1, ups)
+    keep["ypath"] = np.full(max(plen, 1), -1, np.int32)
+    keep["status"] = np.zeros(1, np.int32)
+    job = np.zeros(1, dtype=svb.capi.DENSE)
+    job["costs"], job["del_penalty"], job["bp"], job["csum"] = (keep[k].ctypes.data for k in ("costs", "pen", "bp", "csum"))
+    job["ypath"], job["status_d"] = keep["ypath"].ctypes.data, keep["status"].ctypes.data
+    job["s0"], job["s1"], job["t0"], job["t1"], job["upsample"], job["path_len"] = s0, s1, t0, t1, ups, plen
+    return job, keep, plen
+
+
+def test_host_dense_dp_known_answer(svb, gold):
+    s0, s1 = gold["dense_costs"].shape
+    job, keep, plen = _dense_job(svb, gold["dense_costs"], float(gold["pen"][0]), s0, s1, 0)
+    assert svb.capi.lib().svx_host_dense_dp(job.ctypes.data) == 0
+    assert keep["status"][0] == 0
+    assert np.array_equal(keep["csum"], gold["dense_csum"])
+    assert np.array_equal(keep["bp"].astype(np.int32), gold["dense_bp"])
+    path = gold["path_same"]
+    assert plen == path.shape[0]
+    assert np.array_equal(keep["ypath"], path[:, 1]) and np.array_equal(np.arange(plen) - keep["ypath"], path[:, 0])
+
+
+def _band_job(svb, costs_tab, boff, types, pen, s0, s1, target=None):
+    T, A, B = costs_tab.shape
+    w = B // 2
+    keep = {"costs": np.ascontiguousarray(costs_tab.transpose(1, 0, 2)), "ypath": (boff + w).astype(np.int32),
+            "pen": np.array([pen], np.float64), "bp": np.zeros((A + 2, B), np.uint8),
+            "csum": np.zeros((A + 2, B), np.float64), "recs": np.zeros(s0 + s1 + 2, dtype=svb.capi.REC),
+            "nrecs": np.zeros(1, np.int32), "status": np.zeros(1, np.int32)}
+    job = np.zeros(1, dtype=svb.capi.BAND)
+    for f, k in (("costs", "costs"), ("ypath", "ypath"), ("del_penalty", "pen"), ("bp", "bp"), ("csum", "csum"),
+                 ("recs", "recs"), ("nrecs", "nrecs"), ("status_d", "status")):
+        job[f] = keep[k].ctypes.data
+    job["s0"], job["s1"], job["a_len"], job["band"], job["width_over2"], job["ntypes"] = s0, s1, A, B, w, T
+    job["rec_cap"] = s0 + s1 + 2
+    for t, (x, y) in enumerate(types):
+        job["xo"][0, t], job["yo"][0, t] = x, y
+    job["amax"] = max([2] + [x + y for x, y in types])
+    if target is not None:
+        nlen = svb.capi.lib().svx_path_len(s0, s1, target[0], target[1], 1)
+        keep["next"] = np.full(nlen, -1, np.int32)
+        job["next_ypath"], job["t0"], job["t1"], job["next_len"] = keep["next"].ctypes.data, target[0], target[1], nlen
+    return job, keep
+
+
+def _xy_of(svb, bp, types):
+    tx = np.array([x for x, _ in types] + [0, 1], np.int32)
+    ty = np.array([y for _, y in types] + [1, 0], np.int32)
+    xp = np.full(bp.shape, -42, np.int32)
+    yp = np.full(bp.shape, -42, np.int32)
+    ok = bp != svb.capi.SVX_BP_NONE
+    xp[ok], yp[ok] = tx[bp[ok]], ty[bp[ok]]
+    return xp, yp
+
+
+@pytest.mark.parametrize("tag", [None, "even", "odd"])
+def test_host_banded_dp_known_answer(svb, oracle, gold, tag):
+    types = oracle.alignment_types(4)
+    s0, s1 = gold["unit0"].shape[1], gold["unit1"].shape[1]
+    target = None if tag is None else ((2 * s0, 2 * s1) if tag == "even" else (2 * s0 + 1, 2 * s1 + 1))
+    job, keep = _band_job(svb, gold["sparse_costs"], gold["b_offset"], types, float(gold["sparse_pen"][0]), s0, s1, target)
+    assert svb.capi.lib().svx_host_banded_dp(job.ctypes.data) == 0
+    assert keep["status"][0] == 0
+    assert np.array_equal(keep["csum"], gold["sparse_csum"])
+    xp, yp = _xy_of(svb, keep["bp"], types)
+    assert np.array_equal(xp, gold["sparse_xp"]) and np.array_equal(yp, gold["sparse_yp"])
+    n = int(keep["nrecs"][0])
+    recs = keep["recs"][len(keep["recs"]) - n:]
+    assert np.array_equal(recs["nx"], gold["trace_nx"]) and np.array_equal(recs["ny"], gold["trace_ny"])
+    assert np.array_equal(recs["score"], gold["trace_scores"])
+    has_x = gold["trace_nx"] > 0
+    assert np.array_equal(recs["x_end"][has_x], gold["trace_x_end"][has_x])
+    if tag is not None:
+        path = gold[f"path_up_{tag}"]
+        assert np.array_equal(keep["next"], path[:, 1])
+
+
+@pytest.mark.parametrize("seed,s0,s1,a,w", [(0, 40, 37, 4, 7), (1, 25, 60, 6, 8), (2, 64, 64, 8, 9), (3, 3, 9, 3, 3), (4, 1, 1, 2, 3)])
+def test_host_twins_vs_oracle_random(svb, oracle, ocore, seed, s0, s1, a, w):
+    """Dense twin -> same-level path -> banded twin -> upsampled path, against the oracle chain."""
+    rng = np.random.default_rng(seed)
+    k = a - 1
+    v0 = rng.standard_normal((k, s0, 128)).astype(np.float32)
+    v1 = rng.standard_normal((k, s1, 128)).astype(np.float32)
+    oracle.unit_rows(v0, fast=True)
+    oracle.unit_rows(v1, fast=True)
+    n0 = rng.uniform(0.7, 1.1, (k, s0)).astype(np.float32)
+    n1 = rng.uniform(0.7, 1.1, (k, s1)).astype(np.float32)
+    pen = 0.41
+    costs = ocore.make_dense_costs(v0, v1, n0, n1)
+    cs, bp = ocore.dense_dp(costs, pen)
+    job, keep, plen = _dense_job(svb, costs, pen, s0, s1, 0)
+    assert svb.capi.lib().svx_host_dense_dp(job.ctypes.data) == 0
+    assert np.array_equal(keep["csum"], cs) and np.array_equal(keep["bp"].astype(np.int32), bp)
+    path = oracle.search_path(oracle.dense_backtrace(bp))
+    assert [(i - int(y), int(y)) for i, y in enumerate(keep["ypath"])] == path
+    types = oracle.alignment_types(a)
+    feats, boff = ocore.make_sparse_costs(v0, v1, n0, n1, path, types, w)
+    csum, xp, yp, nbo = ocore.sparse_dp(feats, boff, types, pen, s0, s1)
+    al, sc = oracle.banded_backtrace(csum, xp, yp, nbo, s0, s1)
+    t0, t1 = 2 * s0 + 1, 2 * s1
+    job, keep = _band_job(svb, feats, boff, types, pen, s0, s1, (t0, t1))
+    assert svb.capi.lib().svx_host_banded_dp(job.ctypes.data) == 0
+    assert keep["status"][0] == 0
+    assert np.array_equal(keep["csum"], csum)
+    gx, gy = _xy_of(svb, keep["bp"], types)
+    assert np.array_equal(gx, xp) and np.array_equal(gy, yp)
+    n = int(keep["nrecs"][0])
+    from speech_vecalign_b200.engine import records_to_alignments
+    gal, gsc = records_to_alignments(keep["recs"][len(keep["recs"]) - n:])
+    assert same_alignments(gal, al) and np.array_equal(gsc, sc)
+    up = oracle.double_resolution(al)
+    oracle.extend_to(up, t0, t1)
+    want = oracle.search_path(up)
+    assert [(i - int(y), int(y)) for i, y in enumerate(keep["next"])] == want
+
+
+@pytest.mark.parametrize("c0,c1,t0,t1", [(5, 7, 10, 14), (5, 7, 11, 15), (0, 3, 1, 7), (0, 0, 1, 1), (150, 151, 301, 303)])
+def test_path_len_matches_reference_glue(svb, oracle, c0, c1, t0, t1):
+    al = [([i], [i]) for i in range(min(c0, c1))]
+    al += [([i], []) for i in range(min(c0, c1), c0)] + [([], [i]) for i in range(min(c0, c1), c1)]
+    up = oracle.double_resolution(al)
+    oracle.extend_to(up, t0, t1)
+    assert svb.capi.lib().svx_path_len(c0, c1, t0, t1, 1) == len(oracle.search_path(up))
+    assert svb.capi.lib().svx_path_len(c0, c1, c0, c1, 0) == len(oracle.search_path(al))
+    from speech_vecalign_b200 import engine
+    assert int(engine.path_len(c0, c1, t0, t1, 1)) == len(oracle.search_path(up))
+
+
+# ------------------------------------------------------------------------------------------------
+def test_planner_level_sizes(svb):
+    from speech_vecalign_b200 import engine
+    depth, s0, s1 = engine.level_sizes([237, 2000, 20000, 0, 5, 299], [217, 2000, 20000, 5, 301, 302], 300)
+    assert list(depth) == [0, 3, 7, 0, 0, 1]
+    assert list(s0[1][:4]) == [2000, 1000, 500, 250] and s0[2][7] == 156
+    assert s0[5][1] == 149 and s1[5][1] == 151
+
+
+@pytest.mark.parametrize("n0,n1,a", [(237, 217, 4), (700, 650, 5), (90, 80, 6), (0, 5, 4), (3, 2000, 4)])
+def test_planner_replays_reference_rng_stream(svb, oracle, n0, n1, a):
+    """draw_samples() must leave np.random in exactly the state the reference's vecalign leaves it in
+     — checked against the oracle driver, which is pinned to the reference."""
+    from speech_vecalign_b200 import engine, synth
+    k = a - 1
+    v0, v1 = synth.synth_pair(n0, n1, k, dim=128, seed=1)
+    np.random.seed(77)
+    oracle.vecalign(v0, v1, oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100, fast_host=True)
+    want = np.random.get_state()[1].copy()
+    depth, S0, S1 = engine.level_sizes([n0], [n1], 300)
+    nlev = depth + 1
+    np.random.seed(77)
+    engine.draw_samples(S0[0, :nlev[0]], S1[0, :nlev[0]], np.array([0]), nlev, k, k, 100, 20000, False, False)
+    assert np.array_equal(np.random.get_state()[1], want)

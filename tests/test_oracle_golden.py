@@ -1,0 +1,235 @@
+"""CPU: pins the ORACLE (oracle/ — the checker) against the reference.
+
+Three anchors, strongest first:
+  1. live: oracle vs the real reference (/root/reference Python driver + its own compiled core) on
+     the same seeded inputs — every stack entry identical.  Runs only where /root/reference exists
+     (the build container).
+  2. compiled core: the C restatement (oracle/dp_core_oracle.c) vs the reference's own dp_core
+     compiled into oracle/_ref — bit-exact on random inputs.  Runs wherever oracle/_ref travelled.
+  3. committed fixtures: tests/golden/ (reference outputs written by tests/golden/make_golden.py)
+     — per-function known answers, end-to-end alignments, the shipped example alignment.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, same_alignments
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLDEN, "functions.npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. committed fixtures, function by function (bit-exact)
+# ------------------------------------------------------------------------------------------------
+def test_unit_rows_and_halve(oracle, gold):
+    v = gold["raw0"].copy()
+    oracle.unit_rows(v)
+    assert np.array_equal(v, gold["unit0"])
+    v = gold["raw1"].copy()
+    oracle.unit_rows(v, fast=True)          # vectorised twin used by the big tests
+    assert np.array_equal(v, gold["unit1"])
+    assert np.array_equal(oracle.halve(gold["unit0"].copy()), gold["half0"])
+    assert np.array_equal(oracle.halve(gold["unit0"].copy(), fast=True), gold["half0"])
+
+
+def test_dense_costs_and_dp(ocore, gold):
+    c = ocore.make_dense_costs(gold["unit0"], gold["unit1"], gold["n0"], gold["n1"])
+    assert np.array_equal(c, gold["dense_costs"])
+    cs, bp = ocore.dense_dp(gold["dense_costs"], float(gold["pen"][0]))
+    assert np.array_equal(cs, gold["dense_csum"]) and np.array_equal(bp, gold["dense_bp"])
+
+
+def test_score_path_and_knob(oracle, ocore, gold):
+    out = np.empty(600, np.float32)
+    ocore.score_path(gold["score_x"], gold["score_y"], gold["n0"][0], gold["n1"][0], gold["unit0"][0],
+                     gold["unit1"][0], out)
+    assert np.array_equal(out, gold["score_out"])
+    knob = oracle.PercentileKnob(gold["score_out"], 0, max(gold["score_out"]))
+    pens = np.array([knob.percentile_frac_to_del_penalty(f) for f in gold["knob_fracs"]])
+    assert np.array_equal(pens, gold["knob_pens"])
+
+
+def test_sparse_costs_dp_traceback(oracle, ocore, gold):
+    types = oracle.alignment_types(4)
+    path = [tuple(p) for p in gold["path_same"]]
+    feats, boff = ocore.make_sparse_costs(gold["unit0"], gold["unit1"], gold["n0"], gold["n1"], path, types, 7)
+    assert np.array_equal(feats, gold["sparse_costs"]) and np.array_equal(boff, gold["b_offset"])
+    s0, s1 = gold["unit0"].shape[1], gold["unit1"].shape[1]
+    csum, xp, yp, nbo = ocore.sparse_dp(gold["sparse_costs"], gold["b_offset"], types, float(gold["sparse_pen"][0]), s0, s1)
+    assert np.array_equal(csum, gold["sparse_csum"])
+    assert np.array_equal(xp, gold["sparse_xp"]) and np.array_equal(yp, gold["sparse_yp"])
+    assert np.array_equal(nbo, gold["new_b_offset"])
+    al, sc = oracle.banded_backtrace(csum, xp, yp, nbo, s0, s1)
+    assert [len(x) for x, _ in al] == list(gold["trace_nx"]) and [len(y) for _, y in al] == list(gold["trace_ny"])
+    assert np.array_equal(sc, gold["trace_scores"])
+
+
+def test_search_path_glue(oracle, ocore, gold):
+    dal = oracle.dense_backtrace(gold["dense_bp"])
+    assert oracle.search_path(dal) == [tuple(p) for p in gold["path_same"]]
+    s0, s1 = gold["unit0"].shape[1], gold["unit1"].shape[1]
+    al, _ = oracle.banded_backtrace(gold["sparse_csum"], gold["sparse_xp"], gold["sparse_yp"], gold["new_b_offset"], s0, s1)
+    for t0, t1, tag in [(2 * s0, 2 * s1, "even"), (2 * s0 + 1, 2 * s1 + 1, "odd")]:
+        up = oracle.double_resolution([(list(x), list(y)) for x, y in al])
+        oracle.extend_to(up, t0, t1)
+        assert oracle.search_path(up) == [tuple(p) for p in gold[f"path_up_{tag}"]]
+
+
+def test_alignment_types_order(oracle):
+    # vecalign.py:154-162: x outer, y inner
+    assert oracle.alignment_types(4) == [(1, 1), (1, 2), (1, 3), (2, 1), (2, 2), (3, 1)]
+    assert len(oracle.alignment_types(6)) == 15 and len(oracle.alignment_types(8)) == 28
+    assert oracle.many_to_one_types(3) == [(1, 1), (2, 1), (3, 1)]
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. committed fixtures, end to end
+# ------------------------------------------------------------------------------------------------
+def _e2e_cases():
+    cases = json.load(open(os.path.join(GOLDEN, "e2e.json")))["cases"]
+    return [pytest.param(c, id=f"{c['n0']}x{c['n1']}-a{c['a']}") for c in cases]
+
+
+@pytest.mark.parametrize("case", _e2e_cases())
+def test_oracle_reproduces_reference_e2e(oracle, case):
+    """Alignments identical to the reference's; scores/penalties within 2e-5 (the sample norms go
+    through the host's sgemm, whose summation order depends on the CPU model)."""
+    from speech_vecalign_b200 import synth
+    a, k = case["a"], case["a"] - 1
+    v0, v1 = synth.synth_pair(case["n0"], case["n1"], k, seed=case["seed"])
+    assert abs(float(np.abs(v0).sum()) - case["input_checksum"][0]) <= 1e-3 * case["input_checksum"][0]
+    np.random.seed(case["rng_seed"])
+    st = oracle.vecalign(v0, v1, oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100, fast_host=True)
+    assert same_alignments(st[0]["final_alignments"], case["alignments"])
+    assert np.max(np.abs(st[0]["alignment_scores"] - np.array(case["scores"]))) <= 2e-5
+    pens = [float(st[d]["del_penalty"]) for d in sorted(st)]
+    assert np.allclose(pens, case["del_penalty"], rtol=0, atol=2e-5)
+
+
+def _example_vecs(k):
+    from speech_vecalign_b200 import embedding_utils as eu
+    from speech_vecalign_b200.vecalign import load_ignore_index_file
+    ex = os.path.join(GOLDEN, "example")
+    out = []
+    for lang, ign in (("en", "ignore.src.txt"), ("de", "ignore.tgt.txt")):
+        sent2id, rows = eu.read_in_embeddings(f"{ex}/{lang}.cat_segs.txt", f"{ex}/{lang}.embed", use_stopes=True)
+        lines = open(f"{ex}/{lang}.segments.txt").readlines()
+        out.append(eu.make_doc_embedding(sent2id, rows, lines, k, ignore_indices=load_ignore_index_file(f"{ex}/{ign}"),
+                                         overlap_segments=True))
+    return out
+
+
+@pytest.mark.parametrize("a", [4, 6])
+def test_oracle_on_shipped_example(oracle, a):
+    """BASELINE config 1 (a=4) and the shipped golden alignment (a=6, 156 lines)."""
+    ref = json.load(open(os.path.join(GOLDEN, "example_reference.json")))[f"a{a}"]
+    k = a - 1
+    v0, v1 = _example_vecs(k)
+    assert abs(float(np.abs(v0).sum()) - ref["vecs0_checksum"]) <= 1e-3 * ref["vecs0_checksum"]
+    assert abs(float(np.abs(v1).sum()) - ref["vecs1_checksum"]) <= 1e-3 * ref["vecs1_checksum"]
+    np.random.seed(ref["rng_seed"])
+    st = oracle.vecalign(v0, v1, oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    assert same_alignments(st[0]["final_alignments"], ref["alignments"])
+    assert np.max(np.abs(st[0]["alignment_scores"] - np.array(ref["scores"]))) <= 2e-5
+    if a == 6:
+        from speech_vecalign_b200.vecalign import read_alignments
+        shipped = read_alignments(os.path.join(GOLDEN, "example", "shipped_alignment_a6.txt"))
+        assert len(shipped) == 156
+        assert same_alignments(st[0]["final_alignments"], shipped)
+        file_scores = [float(ln.rsplit(":", 1)[1]) for ln in open(os.path.join(GOLDEN, "example", "shipped_alignment_a6.txt"))]
+        # the shipped file was produced with another numpy / RNG state: loose bound
+        assert np.max(np.abs(st[0]["alignment_scores"] - np.array(file_scores))) <= 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. C restatement vs the reference's own compiled core (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def refcore():
+    from oracle import ref_loader
+    core = ref_loader.ref_core()
+    if core is None:
+        pytest.skip("oracle/_ref not built (make -C oracle ref needs /root/reference)")
+    return core
+
+
+@pytest.mark.parametrize("seed,k,s0,s1,a,w", [(0, 3, 50, 44, 4, 7), (1, 5, 33, 61, 6, 8), (2, 7, 40, 40, 8, 9), (3, 2, 9, 3, 3, 3)])
+def test_c_port_equals_compiled_reference(oracle, ocore, refcore, seed, k, s0, s1, a, w):
+    rng = np.random.default_rng(seed)
+    v0 = rng.standard_normal((k, s0, 256)).astype(np.float32)
+    v1 = rng.standard_normal((k, s1, 256)).astype(np.float32)
+    oracle.unit_rows(v0, fast=True)
+    oracle.unit_rows(v1, fast=True)
+    v0[1:, 0] = 0
+    v1[1:, 0] = 0
+    n0 = rng.uniform(0.6, 1.2, (k, s0)).astype(np.float32)
+    n1 = rng.uniform(0.6, 1.2, (k, s1)).astype(np.float32)
+    c_ref = refcore.make_dense_costs(v0, v1, n0, n1)
+    assert np.array_equal(ocore.make_dense_costs(v0, v1, n0, n1), c_ref)
+    pen = 0.37
+    cs_r, bp_r = refcore.dense_dp(c_ref, pen)
+    cs_o, bp_o = ocore.dense_dp(c_ref, pen)
+    assert np.array_equal(cs_r, cs_o) and np.array_equal(bp_r, bp_o)
+    xi = rng.integers(0, s0, 300).astype(np.int32)
+    yi = rng.integers(0, s1, 300).astype(np.int32)
+    o1, o2 = np.empty(300, np.float32), np.empty(300, np.float32)
+    refcore.score_path(xi, yi, n0[0], n1[0], v0[0], v1[0], o1)
+    ocore.score_path(xi, yi, n0[0], n1[0], v0[0], v1[0], o2)
+    assert np.array_equal(o1, o2)
+    types = oracle.alignment_types(a)
+    path = oracle.search_path(oracle.dense_backtrace(bp_r))
+    f_r, b_r = refcore.make_sparse_costs(v0, v1, n0, n1, path, types, w)
+    f_o, b_o = ocore.make_sparse_costs(v0, v1, n0, n1, path, types, w)
+    assert np.array_equal(f_r, f_o) and np.array_equal(b_r, b_o)
+    r = refcore.sparse_dp(f_r, b_r, types, pen, s0, s1)
+    o = ocore.sparse_dp(f_r, b_r, types, pen, s0, s1)
+    for x, y in zip(r, o):
+        assert np.array_equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. live against the real reference (build container only)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_du():
+    from oracle import ref_loader
+    du = ref_loader.ref_dp_utils()
+    if du is None:
+        pytest.skip("/root/reference not present on this machine")
+    return du
+
+
+@pytest.mark.parametrize("n0,n1,a,seed", [(90, 100, 4, 0), (330, 310, 6, 1), (640, 700, 5, 2), (5, 301, 4, 3), (0, 5, 4, 4), (1, 1, 4, 5)])
+def test_oracle_equals_live_reference(oracle, ref_du, n0, n1, a, seed):
+    from speech_vecalign_b200 import synth
+    k = a - 1
+    v0, v1 = synth.synth_pair(n0, n1, k, dim=256, seed=seed)
+    args = (oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    np.random.seed(seed)
+    ref = ref_du.vecalign(v0.copy(), v1.copy(), *args)
+    st_ref = np.random.get_state()[1].copy()
+    np.random.seed(seed)
+    got = oracle.vecalign(v0.copy(), v1.copy(), *args)
+    assert np.array_equal(st_ref, np.random.get_state()[1]), "RNG stream consumed differently"
+    assert set(ref) == set(got)
+    for d in ref:
+        for key, val in ref[d].items():
+            if key == "del_knob":
+                continue
+            g = got[d][key]
+            if isinstance(val, np.ndarray):
+                assert np.array_equal(val, g, equal_nan=True), (d, key)
+            elif key in ("alignments", "final_alignments"):
+                assert same_alignments(val, g), (d, key)
+            elif key == "searchpath":
+                assert [tuple(p) for p in val] == [tuple(p) for p in g], (d, key)
+            elif key == "alignment_types":
+                assert list(val) == list(g)
+            else:
+                assert val == g, (d, key)
