@@ -117,6 +117,10 @@ typedef struct SvxScoreJob {
     const int32_t *yi;     /* (nsamp) or NULL                                   */
     float *scores;         /* (nsamp) output                                    */
     double *del_penalty;   /* (1) output of svx_del_knob                        */
+    int32_t *perm;         /* (nsamp) scratch or NULL: svx_score_pairs orders the samples by
+                              xi here (device counting sort) so that warps share x rows    */
+    const float *dots;     /* (ne, nf) or NULL: e.f already computed in the reference's order
+                              (SvxDenseJob.dots of the same level); then only gathered      */
     int32_t ne, nf, nsamp;
 } SvxScoreJob;
 SVX_API int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, int dim, int mode,
@@ -137,6 +141,7 @@ typedef struct SvxDenseJob {
     const float *n0;           /* (s0)                                                   */
     const float *n1;           /* (s1)                                                   */
     float *costs;              /* (s0, s1) output of svx_dense_costs                     */
+    float *dots;               /* (s0, s1) or NULL: the raw dot products v0[x].v1[y]     */
     const double *del_penalty; /* (1); narrowed to fp32 as dense_dp(float pen) does      */
     uint8_t *bp;               /* (s0+1, s1+1) backpointers 0/1/2, 4 at the origin       */
     double *csum;              /* (s0+1, s1+1) or NULL (debug/parity only)               */

@@ -29,9 +29,9 @@ NORM = np.dtype([("vecs", _P), ("other", _P), ("idx", _P), ("mbar", _P), ("norms
                  ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32)],
                 align=True)
 SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
-                  ("scores", _P), ("del_penalty", _P),
+                  ("scores", _P), ("del_penalty", _P), ("perm", _P), ("dots", _P),
                   ("ne", np.int32), ("nf", np.int32), ("nsamp", np.int32)], align=True)
-DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("del_penalty", _P),
+DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("dots", _P), ("del_penalty", _P),
                   ("bp", _P), ("csum", _P), ("ypath", _P), ("status_d", _P),
                   ("s0", np.int32), ("s1", np.int32), ("t0", np.int32), ("t1", np.int32),
                   ("upsample", np.int32), ("path_len", np.int32)], align=True)

@@ -305,6 +305,278 @@ __global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Banded DP, standard type set (make_alignment_types(K+1), vecalign.py:154-162; K = 1 for the
+// coarser levels).  One CTA of 4 warps per job.
+//
+//   phase 1  warp 0 runs the recurrence, lane = band slot.  The last K+1 diagonals of fp64
+//            cumulative costs live in REGISTERS; the predecessor of a candidate (dx,dy) on
+//            diagonal aa-(dx+dy) sits in lane  b + (boff(aa) - boff(aa-dx-dy)) - dy,  a shift that
+//            is uniform over the warp, so each candidate is one 64-bit warp shuffle + one DADD
+//            + one compare, with the type loop fully unrolled in the reference's priority order
+//            (types, then (0,1), then (1,0); strict '<' keeps the first minimum).  Warps 1-3
+//            stream the cost diagonals (contiguous T*B floats each) and band offsets into a
+//            shared-memory double buffer.  uint8 backpointers and fp64 csum go to HBM.
+//   phase 2  thread 0 walks the backpointers from (s0,s1) through a shared-memory window of
+//            backpointers + band offsets (reloaded, coalesced, when the walk leaves it) and
+//            writes the integer fields of the alignment records.
+//   phase 3  all threads: scores = clipped csum differences (process_scores), and the search
+//            path of the next finer level, one alignment (+ the deletion run that follows it)
+//            per thread; long slanted segments are expanded by the whole CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBigSeg = 96;      // segments longer than this are expanded cooperatively
+constexpr int kSegQueue = 48;
+
+struct SegQueue {
+    long long xs[kSegQueue], ys[kSegQueue], xw[kSegQueue], yw[kSegQueue];
+    int n;
+};
+
+__device__ __forceinline__ void emit_points(int32_t *ypath, int path_len, long long xs, long long ys, long long xw,
+                                            long long yw, long long first, long long stride)
+{
+    const long long nn = xw + yw;
+    for (long long i = first; i <= nn; i += stride) {
+        int x, y;
+        svx_slant_point(xs, ys, xw, yw, i, &x, &y);
+        if (x + y < path_len) ypath[x + y] = y;
+    }
+}
+
+__device__ __forceinline__ void emit_segment(SegQueue *q, int32_t *ypath, int path_len, long long xs, long long ys,
+                                             long long xw, long long yw)
+{
+    if (xw + yw <= 0) return;
+    if (xw + yw > kBigSeg) {
+        const int slot = atomicAdd(&q->n, 1);
+        if (slot < kSegQueue) {
+            q->xs[slot] = xs; q->ys[slot] = ys; q->xw[slot] = xw; q->yw[slot] = yw;
+            return;
+        }
+    }
+    emit_points(ypath, path_len, xs, ys, xw, yw, 1, 1);
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, int kChunk, int win_diags)
+{
+    constexpr int T = K * (K + 1) / 2;
+    constexpr int NH = K + 1;                  // deepest diagonal a candidate reaches back to
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int wst[5];                     // walk state: x, y, count, status, done
+    __shared__ SegQueue segq;
+    const SvxBandJob &job = jobs[blockIdx.x];
+    const int B = job.band, A = job.a_len, w = job.width_over2;
+    const int s0 = job.s0, s1 = job.s1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nodes_a = A + 2;
+    const int tb = T * B;
+    const int cstride = kChunk * tb + 32;      // +32: lanes >= B read past their diagonal's block
+
+    float *cbuf0 = reinterpret_cast<float *>(smem_raw);
+    float *cbuf1 = cbuf0 + cstride;
+    int *bbuf0 = reinterpret_cast<int *>(cbuf1 + cstride);
+    int *bbuf1 = bbuf0 + kChunk;
+    const double pen = *job.del_penalty;
+
+    auto stage = [&](int c, int first_thread, int nthreads) {
+        const int start = c * kChunk;
+        float *cb = (c & 1) ? cbuf1 : cbuf0;
+        int *bb = (c & 1) ? bbuf1 : bbuf0;
+        const int lo = start - 2, hi = min(start + kChunk, nodes_a) - 2;   // cost diagonals [lo, hi)
+        const int clo = max(lo, 0), chi = min(hi, A);
+        if (chi > clo) {
+            const float *src = job.costs + (size_t)clo * tb;
+            float *dst = cb + (size_t)(clo - lo) * tb;
+            const int n = (chi - clo) * tb;
+            for (int i = first_thread; i < n; i += nthreads) dst[i] = __ldg(src + i);
+        }
+        for (int i = first_thread; i < kChunk; i += nthreads) {
+            const int aa = start + i;
+            bb[i] = aa < nodes_a ? svx_boff_out(job.ypath, aa, w) : 0;
+        }
+    };
+
+    // ---- phase 1 ------------------------------------------------------------------------------
+    double hist[NH + 1];     // hist[s] = csum of this lane's slot on diagonal aa - s
+    int bofh[NH + 1];        // bofh[s] = b_offset_out[aa - s]
+#pragma unroll
+    for (int s = 0; s <= NH; ++s) { hist[s] = INFINITY; bofh[s] = 0; }
+
+    const int nchunks = (nodes_a + kChunk - 1) / kChunk;
+    stage(0, tid, blockDim.x);
+    __syncthreads();
+    for (int c = 0; c < nchunks; ++c) {
+        if (warp != 0) {
+            if (c + 1 < nchunks) stage(c + 1, tid - 32, blockDim.x - 32);
+        } else {
+            const float *cb = (c & 1) ? cbuf1 : cbuf0;
+            const int *bo = (c & 1) ? bbuf1 : bbuf0;
+            const int start = c * kChunk;
+            const int end = min(start + kChunk, nodes_a);
+#pragma unroll 2
+            for (int aa = start; aa < end; ++aa) {
+                const int bo0 = bo[aa - start];
+                bofh[0] = bo0;
+                const int yy = lane + bo0, xx = aa - yy;
+                const float *crow = cb + (size_t)(aa - start) * tb + lane;
+                // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the
+                // deletions - reference quirk, dp_core.pyx:382,390)
+                const bool cell_ok = xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && aa - 2 < A;
+                double best = INFINITY;
+                int code = SVX_BP_NONE;
+                int t = 0;
+#pragma unroll
+                for (int x = 1; x <= K; ++x) {
+#pragma unroll
+                    for (int y = 1; x + y <= K + 1; ++y, ++t) {
+                        const int s = x + y;
+                        const int src = lane + (bo0 - bofh[s]) - y;
+                        const double pv = __shfl_sync(0xffffffffu, hist[s], src & 31);
+                        const double tot = __dadd_rn(pv, (double)crow[t * B]);
+                        const bool ok = cell_ok && xx >= x && yy >= y && src >= 0 && src < B;
+                        if (ok && tot < best) { best = tot; code = t; }
+                    }
+                }
+                {
+                    const double hp = __dadd_rn(hist[1], pen);
+                    const int d1 = bo0 - bofh[1];
+                    int src = lane + d1 - 1;                                   // (0,1): consume y
+                    double tot = __shfl_sync(0xffffffffu, hp, src & 31);
+                    bool ok = cell_ok && yy >= 1 && src >= 0 && src < B;
+                    if (ok && tot < best) { best = tot; code = T; }
+                    src = lane + d1;                                           // (1,0): consume x
+                    tot = __shfl_sync(0xffffffffu, hp, src & 31);
+                    ok = cell_ok && xx >= 1 && src >= 0 && src < B;
+                    if (ok && tot < best) { best = tot; code = T + 1; }
+                }
+                if (xx == 0 && yy >= 0 && yy <= s1) { best = __dmul_rn(pen, (double)yy); code = T; }
+                else if (yy == 0 && xx >= 0 && xx <= s0) { best = __dmul_rn(pen, (double)xx); code = T + 1; }
+                if (lane < B) {
+                    job.bp[(size_t)aa * B + lane] = (uint8_t)code;
+                    job.csum[(size_t)aa * B + lane] = best;
+                }
+#pragma unroll
+                for (int s = NH; s >= 2; --s) { hist[s] = hist[s - 1]; bofh[s] = bofh[s - 1]; }
+                hist[1] = best;
+                bofh[1] = bo0;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 2: backpointer walk through a shared-memory window ---------------------------------
+    int *wboff = reinterpret_cast<int *>(smem_raw);
+    uint8_t *wbp = reinterpret_cast<uint8_t *>(wboff + win_diags);
+    const int cap = job.rec_cap;
+    if (tid == 0) {
+        wst[0] = s0; wst[1] = s1; wst[2] = 0;
+        wst[3] = (s0 + s1 >= nodes_a) ? SVX_ST_LEFT_BAND : SVX_ST_OK;
+        wst[4] = (wst[3] != SVX_ST_OK) || (s0 == 0 && s1 == 0);
+        segq.n = 0;
+    }
+    __syncthreads();
+    while (!wst[4]) {
+        const int top = wst[0] + wst[1];
+        const int hi = top + 1, lo = max(0, hi - win_diags);
+        for (int i = tid; i < hi - lo; i += blockDim.x) wboff[i] = svx_boff_out(job.ypath, lo + i, w);
+        const uint8_t *bsrc = job.bp + (size_t)lo * B;
+        for (int i = tid; i < (hi - lo) * B; i += blockDim.x) wbp[i] = bsrc[i];
+        __syncthreads();
+        if (tid == 0) {
+            int x = wst[0], y = wst[1], cnt = wst[2], st = SVX_ST_OK;
+            int a = x + y;
+            int b = y - wboff[a - lo];
+            if (b < 0 || b >= B) st = SVX_ST_LEFT_BAND;
+            while (st == SVX_ST_OK && !(x == 0 && y == 0)) {
+                const int code = wbp[(a - lo) * B + b];
+                if (code > T + 1) { st = SVX_ST_NO_BACKPTR; break; }
+                int dx, dy;
+                if (code == T) { dx = 0; dy = 1; }
+                else if (code == T + 1) { dx = 1; dy = 0; }
+                else {            // x outer, y inner: row x holds K+1-x types
+                    int xq = 1, rem = code;
+                    while (rem >= K + 1 - xq) { rem -= K + 1 - xq; ++xq; }
+                    dx = xq; dy = rem + 1;
+                }
+                const int px = x - dx, py = y - dy;
+                if (px < 0 || py < 0) { st = SVX_ST_LEFT_BAND; break; }      // reference: 'traceback bug'
+                const int pa = px + py;
+                if (pa < lo) break;                                          // window exhausted
+                const int pb = py - wboff[pa - lo];
+                if (pb < 0 || pb >= B) { st = SVX_ST_LEFT_BAND; break; }
+                if (cnt < cap) {
+                    int *r = reinterpret_cast<int *>(job.recs + (cap - 1 - cnt));
+                    r[0] = x; r[1] = y; r[2] = dx; r[3] = dy;
+                } else st |= SVX_ST_OVERFLOW;
+                ++cnt;
+                x = px; y = py; a = pa; b = pb;
+            }
+            wst[0] = x; wst[1] = y; wst[2] = cnt; wst[3] = st;
+            wst[4] = (st != SVX_ST_OK) || (x == 0 && y == 0);
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: scores and the next level's search path -------------------------------------------
+    const int n = min(wst[2], cap), status = wst[3];
+    SvxAlignRec *recs = job.recs + (cap - n);                // document order
+    for (int i = tid; i < n; i += blockDim.x) {
+        const SvxAlignRec r = recs[i];
+        const int a = r.x_end + r.y_end, pa = a - r.nx - r.ny;
+        const int b = r.y_end - svx_boff_out(job.ypath, a, w);
+        const int pb = (r.y_end - r.ny) - svx_boff_out(job.ypath, pa, w);
+        double sc = __dsub_rn(job.csum[(size_t)a * B + b], job.csum[(size_t)pa * B + pb]);   // np.diff
+        if (sc < 0.0) sc = 0.0;                                  // np.clip(a_min=0); NaN stays NaN
+        if (r.nx == 0 || r.ny == 0) sc = 0.0;
+        else sc = __ddiv_rn(__ddiv_rn(sc, (double)r.nx), (double)r.ny);
+        recs[i].score = sc;
+    }
+    if (job.next_ypath && status == SVX_ST_OK) {
+        int32_t *np_ = job.next_ypath;
+        const int plen = job.next_len;
+        // extend_alignments (dp_utils.py:228-258) on the upsampled ids
+        const int xmax = s0 > 0 ? 2 * s0 - 1 : 0, ymax = s1 > 0 ? 2 * s1 - 1 : 0;
+        const int lenx = job.t0 - xmax > 0 ? job.t0 - xmax : 0;
+        const int leny = job.t1 - ymax > 0 ? job.t1 - ymax : 0;
+        long long ext_x = 0, ext_y = 0;          // joins the trailing deletion run
+        if (lenx > 0 && leny > 0) {
+            if (tid == 0) emit_segment(&segq, np_, plen, 2LL * s0, 2LL * s1, lenx, leny);
+        } else if (lenx == 0) ext_y = leny;
+        else ext_x = lenx;
+        for (int i = tid - 1; i < n; i += blockDim.x) {
+            // i == -1: the deletion run at the document start (finish()); i >= 0: alignment i and the
+            // deletion run that follows it in document order
+            long long sx = 0, sy = 0;
+            if (i >= 0) {
+                const SvxAlignRec r = recs[i];
+                if (r.nx == 0 || r.ny == 0) continue;
+                emit_segment(&segq, np_, plen, 2LL * (r.x_end - r.nx), 2LL * (r.y_end - r.ny), 2LL * r.nx, 2LL * r.ny);
+                sx = 2LL * r.x_end; sy = 2LL * r.y_end;
+            }
+            long long px = 0, py = 0;
+            int j = i + 1;
+            for (; j < n; ++j) {
+                const int nx = recs[j].nx, ny = recs[j].ny;
+                if (nx > 0 && ny > 0) break;
+                px += 2LL * nx; py += 2LL * ny;
+            }
+            if (j == n) { px += ext_x; py += ext_y; }
+            emit_segment(&segq, np_, plen, sx, sy, px, py);
+        }
+        __syncthreads();
+        const int nq = min(segq.n, kSegQueue);
+        for (int qi = 0; qi < nq; ++qi)
+            emit_points(np_, plen, segq.xs[qi], segq.ys[qi], segq.xw[qi], segq.yw[qi], 1 + tid, blockDim.x);
+        if (tid == 0 && plen > 0) np_[0] = 0;
+    }
+    if (tid == 0) {
+        *job.status_d = status;
+        if (job.nrecs) *job.nrecs = wst[2];
+    }
+}
+
 inline bool is_standard_types(const SvxBandJob &j, int *k_out)
 {
     // make_alignment_types(a): x outer 1..a-1, y inner, x+y <= a  -> K = a-1, T = K(K+1)/2
@@ -399,10 +671,34 @@ static inline int ring_size(int amax)
     return r;
 }
 
+template <int K>
+static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax_len, cudaStream_t st)
+{
+    constexpr int T = K * (K + 1) / 2;
+    const int tb = T * bmax;
+    int chunk = (int)((64 * 1024) / ((size_t)2 * tb * sizeof(float)));
+    chunk = chunk > kMaxChunk ? kMaxChunk : (chunk < 4 ? 4 : chunk);
+    const size_t dp_bytes = (size_t)2 * (chunk * tb + 32) * sizeof(float) + (size_t)2 * chunk * sizeof(int);
+    // walk window: whole job when it fits in ~96 KB, otherwise 96 KB windows
+    const int per_diag = bmax + (int)sizeof(int);
+    int win = amax_len + 2;
+    const int win_cap = (96 * 1024) / per_diag;
+    if (win > win_cap) win = win_cap;
+    if (win < 64) win = 64;
+    const size_t walk_bytes = (size_t)win * per_diag + 16;
+    const size_t smem = dp_bytes > walk_bytes ? dp_bytes : walk_bytes;
+    auto kern = k_banded_dp_tri<K>;
+    if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<njobs, 128, smem, st>>>(jobs_d, chunk, win);
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
 extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, int njobs, void *stream)
 {
     if (njobs <= 0) return SVX_OK;
-    int amax = 2, tbmax = 0, bmax = 0;
+    int amax = 2, tbmax = 0, bmax = 0, alen_max = 0, K = 0;
+    bool standard = true;
     for (int j = 0; j < njobs; ++j) {
         const SvxBandJob &jb = jobs_h[j];
         SVX_REQUIRE(jb.band >= 2 && jb.band <= 32, SVX_ERR_UNSUPPORTED, "svx_banded_dp: band %d must be in [2,32]", jb.band);
@@ -411,7 +707,25 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
         for (int t = 0; t < jb.ntypes; ++t) if (jb.xo[t] + jb.yo[t] > amax) amax = jb.xo[t] + jb.yo[t];
         if (jb.ntypes * jb.band > tbmax) tbmax = jb.ntypes * jb.band;
         if (jb.band > bmax) bmax = jb.band;
+        if (jb.a_len > alen_max) alen_max = jb.a_len;
+        // the register/shuffle kernel needs: the standard type set (same K for the whole launch),
+        // one band width, and record storage
+        int kk = 0;
+        SvxBandJob probe = jb;
+        probe.k0 = probe.k1 = 64;          // is_standard_types only checks the list itself here
+        if (!(is_standard_types(probe, &kk) && (K == 0 || kk == K) && jb.band == jobs_h[0].band && jb.recs)) standard = false;
+        else K = kk;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (standard) {
+        switch (K) {
+#define CASE(KK) case KK: return launch_dp_tri<KK>(jobs_d, njobs, bmax, alen_max, st);
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
+#undef CASE
+            default: break;
+        }
+    }
+    // any other type list: generic kernel (shared-memory ring, run-time type loop)
     const int R = ring_size(amax);
     int chunk = tbmax > 0 ? (int)((96 * 1024) / ((size_t)2 * tbmax * sizeof(float))) : kMaxChunk;
     chunk = chunk > kMaxChunk ? kMaxChunk : (chunk < 2 ? 2 : chunk);
@@ -420,7 +734,7 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
     SVX_REQUIRE(smem <= 220 * 1024, SVX_ERR_UNSUPPORTED, "svx_banded_dp: %zu B of shared memory needed", smem);
     if (smem > 48 * 1024)
         SVX_CUDA_OK(cudaFuncSetAttribute(k_banded_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_banded_dp<<<njobs, 128, smem, (cudaStream_t)stream>>>(jobs_d, R, chunk);
+    k_banded_dp<<<njobs, 128, smem, st>>>(jobs_d, R, chunk);
     SVX_LAUNCH_CHECK();
     return SVX_OK;
 }

@@ -69,7 +69,10 @@ __global__ void __launch_bounds__(256) k_dense_costs(const SvxDenseJob *jobs, in
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const int y = y0 + tx + 16 * j;
-            if (y < job.s1) job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(acc[i][j], nx, job.n1[y]);
+            if (y < job.s1) {
+                job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(acc[i][j], nx, job.n1[y]);
+                if (job.dots) job.dots[(size_t)x * job.s1 + y] = acc[i][j];
+            }
         }
     }
 }

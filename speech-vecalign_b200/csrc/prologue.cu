@@ -207,32 +207,80 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) k_norms_gemv(const SvxNormJ
 
 // ---------------------------------------------------------------------------------------------
 // sampled pair scores: one thread per sample, the dot product in the reference's order.
+//
+// The samples are random (x, y) row pairs (np.random.choice draws), so a warp would touch 64
+// different 4 KB rows per step.  k_sort_samples orders each job's samples by x with a counting
+// sort in shared memory (one CTA per job; results are written back by original sample index, so
+// the order inside a bucket is irrelevant): consecutive threads then share their x row
+// (broadcast / L1 hits) and only the y row is a per-thread stream, which halves the L2->SM
+// traffic that bounds this kernel.  When the job carries the dense dot matrix of its level
+// (`dots`, coarsest level) the score is a gather.
 // ---------------------------------------------------------------------------------------------
+constexpr int kSortMaxRows = 16384;      // counters of one job in shared memory (64 KB)
+
+__global__ void __launch_bounds__(512) k_sort_samples(const SvxScoreJob *jobs)
+{
+    extern __shared__ int cnt[];         // ne counters, then the running offsets
+    __shared__ int wsum[16];
+    const SvxScoreJob job = jobs[blockIdx.x];
+    if (!job.perm || !job.xi || job.dots || job.ne > kSortMaxRows || job.nsamp <= 0) return;
+    const int ne = job.ne, n = job.nsamp, tid = threadIdx.x;
+    for (int i = tid; i < ne; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) atomicAdd(&cnt[job.xi[i]], 1);
+    __syncthreads();
+    // exclusive scan of cnt[0..ne): each thread owns a contiguous slice
+    const int per = (ne + blockDim.x - 1) / blockDim.x;
+    const int lo = min(tid * per, ne), hi = min(lo + per, ne);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += cnt[i];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if ((tid & 31) >= off) incl += v;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int wq = 0; wq < (tid >> 5); ++wq) base += wsum[wq];
+    for (int i = lo; i < hi; ++i) { const int c = cnt[i]; cnt[i] = base; base += c; }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) job.perm[atomicAdd(&cnt[job.xi[i]], 1)] = i;
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(128) k_score_pairs(const SvxScoreJob *jobs, int dim)
 {
     const SvxScoreJob job = jobs[blockIdx.y];
-    const int i = blockIdx.x * 128 + threadIdx.x;
+    int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= job.nsamp) return;
     int xi, yi;
-    if (job.xi) { xi = job.xi[i]; yi = job.yi[i]; }
-    else { xi = i / job.nf; yi = i % job.nf; }
-    const float *a = job.e + (size_t)xi * dim;
-    const float *b = job.f + (size_t)yi * dim;
+    if (job.xi) {
+        if (job.perm && !job.dots && job.ne <= kSortMaxRows) i = job.perm[i];
+        xi = job.xi[i]; yi = job.yi[i];
+    } else { xi = i / job.nf; yi = i % job.nf; }
     float dot = 0.0f;
-    for (int d = 0; d < dim; d += 8) {
-        const float4 a0 = ldg_f4(a + d), a1 = ldg_f4(a + d + 4);
-        const float4 b0 = ldg_f4(b + d), b1 = ldg_f4(b + d + 4);
-        if (EXACT) {
-            dot = __fadd_rn(dot, __fmul_rn(a0.x, b0.x)); dot = __fadd_rn(dot, __fmul_rn(a0.y, b0.y));
-            dot = __fadd_rn(dot, __fmul_rn(a0.z, b0.z)); dot = __fadd_rn(dot, __fmul_rn(a0.w, b0.w));
-            dot = __fadd_rn(dot, __fmul_rn(a1.x, b1.x)); dot = __fadd_rn(dot, __fmul_rn(a1.y, b1.y));
-            dot = __fadd_rn(dot, __fmul_rn(a1.z, b1.z)); dot = __fadd_rn(dot, __fmul_rn(a1.w, b1.w));
-        } else {
-            dot = fmaf(a0.x, b0.x, dot); dot = fmaf(a0.y, b0.y, dot);
-            dot = fmaf(a0.z, b0.z, dot); dot = fmaf(a0.w, b0.w, dot);
-            dot = fmaf(a1.x, b1.x, dot); dot = fmaf(a1.y, b1.y, dot);
-            dot = fmaf(a1.z, b1.z, dot); dot = fmaf(a1.w, b1.w, dot);
+    if (job.dots) {
+        dot = job.dots[(size_t)xi * job.nf + yi];
+    } else {
+        const float *a = job.e + (size_t)xi * dim;
+        const float *b = job.f + (size_t)yi * dim;
+#pragma unroll 2
+        for (int d = 0; d < dim; d += 8) {
+            const float4 a0 = ldg_f4(a + d), a1 = ldg_f4(a + d + 4);
+            const float4 b0 = ldg_f4(b + d), b1 = ldg_f4(b + d + 4);
+            if (EXACT) {
+                dot = __fadd_rn(dot, __fmul_rn(a0.x, b0.x)); dot = __fadd_rn(dot, __fmul_rn(a0.y, b0.y));
+                dot = __fadd_rn(dot, __fmul_rn(a0.z, b0.z)); dot = __fadd_rn(dot, __fmul_rn(a0.w, b0.w));
+                dot = __fadd_rn(dot, __fmul_rn(a1.x, b1.x)); dot = __fadd_rn(dot, __fmul_rn(a1.y, b1.y));
+                dot = __fadd_rn(dot, __fmul_rn(a1.z, b1.z)); dot = __fadd_rn(dot, __fmul_rn(a1.w, b1.w));
+            } else {
+                dot = fmaf(a0.x, b0.x, dot); dot = fmaf(a0.y, b0.y, dot);
+                dot = fmaf(a0.z, b0.z, dot); dot = fmaf(a0.w, b0.w, dot);
+                dot = fmaf(a1.x, b1.x, dot); dot = fmaf(a1.y, b1.y, dot);
+                dot = fmaf(a1.z, b1.z, dot); dot = fmaf(a1.w, b1.w, dot);
+            }
         }
     }
     job.scores[i] = svx_pair_score(dot, job.norm_e[xi], job.norm_f[yi]);
@@ -368,6 +416,18 @@ extern "C" int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *job
     SVX_REQUIRE(dim > 0 && dim % 8 == 0, SVX_ERR_UNSUPPORTED, "svx_score_pairs: dim %d must be a multiple of 8", dim);
     if (njobs <= 0) return SVX_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    int sort_rows = 0;
+    for (int j = 0; j < njobs; ++j) {
+        const SvxScoreJob &jb = jobs_h[j];
+        if (jb.perm && jb.xi && !jb.dots && jb.ne <= kSortMaxRows && jb.ne > sort_rows) sort_rows = jb.ne;
+    }
+    if (sort_rows > 0) {
+        const size_t smem = (size_t)sort_rows * sizeof(int);
+        if (smem > 48 * 1024)
+            SVX_CUDA_OK(cudaFuncSetAttribute(k_sort_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_sort_samples<<<njobs, 512, smem, st>>>(jobs_d);
+        SVX_LAUNCH_CHECK();
+    }
     for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
         const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
         int ms = 0;

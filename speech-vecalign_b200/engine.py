@@ -214,7 +214,9 @@ class BatchRun:
         o["mbar0"] = ar.take(np.full(R, D * 8))
         o["mbar1"] = ar.take(np.full(R, D * 8))
         o["scores"] = ar.take(nsamp * 4)
+        o["perm"] = ar.take(np.where(has_draw & ~is_top, nsamp * 4, 0))
         o["dcost"] = ar.take(np.where(is_top, rs0 * rs1 * 4, 0))
+        o["ddots"] = ar.take(np.where(is_top, rs0 * rs1 * 4, 0))
         o["dbp"] = ar.take(np.where(is_top, (rs0 + 1) * (rs1 + 1), 0))
         o["dcsum"] = ar.take(np.where(is_top & bool(keep_dense_csum), (rs0 + 1) * (rs1 + 1) * 8, 0))
         o["ypath"] = ar.take(A * 4)
@@ -294,6 +296,9 @@ class BatchRun:
         sj["xi"] = np.where(has_draw[ssel], ptr("xi")[ssel], 0)
         sj["yi"] = np.where(has_draw[ssel], ptr("yi")[ssel], 0)
         sj["scores"], sj["del_penalty"] = ptr("scores")[ssel], ptr("delpen")[ssel]
+        # coarsest level: the dense cost kernel has already produced every dot product of the level
+        sj["dots"] = np.where(is_top[ssel], ptr("ddots")[ssel], 0)
+        sj["perm"] = np.where(has_draw[ssel] & ~is_top[ssel], ptr("perm")[ssel], 0)
         sj["ne"], sj["nf"], sj["nsamp"] = rs0[ssel], rs1[ssel], nsamp[ssel]
         self.score_jobs = sj
 
@@ -302,6 +307,7 @@ class BatchRun:
         dj = np.zeros(P, dtype=capi.DENSE)
         dj["v0"], dj["v1"], dj["n0"], dj["n1"] = vec0[top], vec1[top], ptr("norms0")[top], ptr("norms1")[top]
         dj["costs"], dj["del_penalty"], dj["bp"] = ptr("dcost")[top], ptr("delpen")[top], ptr("dbp")[top]
+        dj["dots"] = ptr("ddots")[top]
         dj["csum"] = ptr("dcsum")[top] if keep_dense_csum else 0
         dj["ypath"] = ptr("ypath")[tgt]
         dj["status_d"] = ptr("status")[top] + np.uint64(4)
@@ -423,9 +429,9 @@ class BatchRun:
         for i in range(len(self.down_jobs)):
             self._call(L.svx_downsample, "svx_downsample", ("down", i), D)
         self._call(L.svx_sample_norms, "svx_sample_norms", "norm", D)
+        self._call(L.svx_dense_costs, "svx_dense_costs", "dense", D, mode)
         self._call(L.svx_score_pairs, "svx_score_pairs", "score", D, mode)
         self._call(L.svx_del_knob, "svx_del_knob", "score", self.frac)
-        self._call(L.svx_dense_costs, "svx_dense_costs", "dense", D, mode)
         self._call(L.svx_dense_dp, "svx_dense_dp", "dense")
         for s, groups in enumerate(self.band_stages):
             for g in range(len(groups)):
