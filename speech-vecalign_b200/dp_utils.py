@@ -53,7 +53,7 @@ def _to_device(v, dev):
 
 def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                    costs_sample_size, num_samps_for_norm, cost_mode="exact", debug=False, writeback=False,
-                   norms0=None, norms1=None, sync=True, output="stack", seeds=None):
+                   norms0=None, norms1=None, sync=True, output="stack", seeds=None, streams=None):
     """Align many document pairs in one pass over the GPU.
 
     pairs: sequence of (vecs0, vecs1), each (K, N, D) fp32 numpy array or torch tensor (host or
@@ -63,6 +63,8 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
     order, 'del_penalty': [per level], 'nrecs', 'status'}) without building Python lists.
     seeds: optional per-pair np.random seeds (np.random.seed(seeds[p]) before pair p's draws), which
     makes every pair's result independent of batch order and of the multi-GPU partition.
+    streams: pair groups enqueued on separate CUDA streams (default 4 for batches of >= 8 pairs);
+    pairs are independent, so results do not depend on it.
     """
     if width_over2 < 3:
         logger.warning('width_over2 was set to %d, which does not make sense. increasing to 3.', width_over2)
@@ -94,7 +96,7 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
                    k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                    costs_sample_size, num_samps_for_norm, dev, cost_mode=_MODES[cost_mode],
                    norms0=norms0, norms1=norms1, keep_dense_csum=debug, seeds=seeds)
-    run.run()
+    run.run(ngroups=(4 if len(dv) >= 8 else 1) if streams is None else int(streams))
     if not sync:
         return run
     res = run.results()

@@ -276,7 +276,7 @@ class BatchRun:
             dj["k"][0::2], dj["n"][0::2] = self.k0, rs0[sel - 1]
             dj["in"][1::2], dj["out"][1::2], dj["mean"][1::2] = vec1[sel - 1], vec1[sel], ptr("mean1")[sel]
             dj["k"][1::2], dj["n"][1::2] = self.k1, rs1[sel - 1]
-            self.down_jobs.append(dj)
+            self.down_jobs.append((dj, np.repeat(rp[sel], 2)))
 
         skip0 = is_l0 & (norms0 is not None)
         skip1 = is_l0 & (norms1 is not None)
@@ -288,7 +288,10 @@ class BatchRun:
         a_["k"], a_["n"], a_["ko"], a_["no"], a_["per"] = self.k0, rs0[sel0], self.k1, rs1[sel0], per1
         b_["vecs"], b_["other"], b_["idx"], b_["mbar"], b_["norms"] = vec1[sel1], vec0[sel1], ptr("idx1")[sel1], ptr("mbar1")[sel1], ptr("norms1")[sel1]
         b_["k"], b_["n"], b_["ko"], b_["no"], b_["per"] = self.k1, rs1[sel1], self.k0, rs0[sel1], per0
-        self.norm_jobs = nj
+        nj_pair = np.concatenate([rp[sel0], rp[sel1]])
+        order = np.argsort(nj_pair, kind="stable")       # pair-major so that a pair range is a job range
+        self.norm_jobs = nj[order]
+        nj_pair = nj_pair[order]
 
         ssel = np.nonzero(nsamp > 0)[0]
         sj = np.zeros(ssel.size, dtype=capi.SCORE)
@@ -350,31 +353,31 @@ class BatchRun:
                     bj["ntypes"], bj["xo"], bj["yo"], bj["amax"] = 1, xo1, yo1, 2
                     bj["next_ypath"] = ptr("ypath")[sel - 1]
                     bj["t0"], bj["t1"], bj["next_len"] = rs0[sel - 1], rs1[sel - 1], A[sel - 1]
-                groups.append(bj)
+                groups.append((bj, rp[sel]))
             self.band_stages.append(groups)
 
         # pack descriptors into the staging buffer
         self._job_views = {}
         cur = self._jobs_off
 
-        def pack(name, arr):
+        def pack(name, arr, pairs):
             nonlocal cur
             nb = arr.nbytes
             cur = (cur + 15) // 16 * 16
             assert cur + nb <= self._jobs_off + self._jobs_cap, "descriptor region too small"
             stage[cur:cur + nb] = arr.view(np.uint8).ravel()
-            self._job_views[name] = (self.base + cur, arr)
+            self._job_views[name] = (self.base + cur, arr, np.asarray(pairs, dtype=np.int64))
             cur += nb
 
-        pack("rows", rows)
-        for i, dj_ in enumerate(self.down_jobs):
-            pack(("down", i), dj_)
-        pack("norm", self.norm_jobs)
-        pack("score", self.score_jobs)
-        pack("dense", self.dense_jobs)
+        pack("rows", rows, np.repeat(np.arange(P), 2))
+        for i, (dj_, pr_) in enumerate(self.down_jobs):
+            pack(("down", i), dj_, pr_)
+        pack("norm", self.norm_jobs, nj_pair)
+        pack("score", self.score_jobs, rp[ssel])
+        pack("dense", self.dense_jobs, np.arange(P))
         for s, groups in enumerate(self.band_stages):
-            for g, bj in enumerate(groups):
-                pack(("band", s, g), bj)
+            for g, (bj, pr_) in enumerate(groups):
+                pack(("band", s, g), bj, pr_)
         self._stage = torch.from_numpy(stage)
         self.arena[:host_end].copy_(self._stage, non_blocking=False)
         if norms0 is not None:
@@ -391,19 +394,24 @@ class BatchRun:
         return self.arena[int(off):int(off) + int(nbytes)].cpu().numpy().view(dtype)
 
     def _call(self, fn, name, key, *extra):
-        dptr, arr = self._job_views[key]
-        if arr.shape[0] == 0:
+        dptr, arr, pairs = self._job_views[key]
+        lo, hi = 0, arr.shape[0]
+        if self._pair_range is not None:
+            lo, hi = (int(v) for v in np.searchsorted(pairs, self._pair_range))
+        if hi <= lo:
             return
+        dptr += lo * arr.dtype.itemsize
+        hp = capi.hptr(arr) + lo * arr.dtype.itemsize
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         if self._events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            capi.check(fn(dptr, capi.hptr(arr), arr.shape[0], *extra, stream), name)
+            capi.check(fn(dptr, hp, hi - lo, *extra, stream), name)
             e1.record()
             self._events.append((name if not isinstance(key, tuple) or key[0] != "band" else
                                  name + ("_level0" if self._band_is_l0(key) else "_coarse"), e0, e1))
             return
-        capi.check(fn(dptr, capi.hptr(arr), arr.shape[0], *extra, stream), name)
+        capi.check(fn(dptr, hp, hi - lo, *extra, stream), name)
 
     def _band_is_l0(self, key):
         return bool(self._job_views[key][1]["ntypes"][0] == len(self.types) and
@@ -419,10 +427,11 @@ class BatchRun:
         return out
 
     _events = None
+    _pair_range = None
+    _streams = None
 
-    def run(self, timing=False):
-        """Enqueue the whole batch on the current stream (asynchronous)."""
-        self._events = [] if timing else None
+    def _enqueue_chain(self):
+        """The whole path for the pairs in self._pair_range (all pairs if None) on the current stream."""
         L = capi.lib()
         D, mode = self.dim, self.cost_mode
         self._call(L.svx_normalize_rows, "svx_normalize_rows", "rows", D)
@@ -438,6 +447,44 @@ class BatchRun:
                 self._call(L.svx_banded_costs, "svx_banded_costs", ("band", s, g), D, mode)
             for g in range(len(groups)):
                 self._call(L.svx_banded_dp, "svx_banded_dp", ("band", s, g))
+
+    def pair_groups(self, ngroups):
+        """Contiguous pair ranges of roughly equal work (bytes of level-0 rows)."""
+        ngroups = max(1, min(int(ngroups), self.P))
+        l0 = self.first
+        work = np.cumsum((self.rs0[l0] + self.rs1[l0]).astype(np.float64) + 1.0)
+        cuts = np.searchsorted(work, work[-1] * np.arange(1, ngroups) / ngroups, side="left") + 1
+        b = np.unique(np.concatenate([[0], np.minimum(cuts, self.P), [self.P]]))
+        return [(int(b[i]), int(b[i + 1])) for i in range(len(b) - 1)]
+
+    def run(self, timing=False, ngroups=1):
+        """Enqueue the whole batch (asynchronous).  ngroups > 1 splits the pairs into contiguous
+        groups, each running its own kernel chain on its own CUDA stream (forked from / joined to the
+        current stream with events): the latency-bound kernels of one group (wavefront DPs, knob)
+        then overlap the bandwidth- and FP32-bound kernels of the others.  Pairs are independent, so
+        the result does not depend on the grouping."""
+        self._events = [] if timing else None
+        if ngroups <= 1 or self.P <= 1:
+            self._pair_range = None
+            self._enqueue_chain()
+            return
+        groups = self.pair_groups(ngroups)
+        if self._streams is None or len(self._streams) < len(groups):
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(len(groups))]
+        cur = torch.cuda.current_stream(self.dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        try:
+            for st, pr in zip(self._streams, groups):
+                st.wait_event(fork)
+                self._pair_range = pr
+                with torch.cuda.stream(st):
+                    self._enqueue_chain()
+                    done = torch.cuda.Event()
+                    done.record(st)
+                cur.wait_event(done)
+        finally:
+            self._pair_range = None
 
     # ------------------------------------------------------------------------------------------
     def algorithmic_bytes(self):

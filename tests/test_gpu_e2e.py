@@ -153,3 +153,29 @@ def test_errors_mirror_reference(svb):
         svb.dp_utils.vecalign(v, v.copy(), [(1, 1)], 0.2, 7, 300, 20000, 100, norms0=np.ones((2, 4), np.float32))
     with pytest.raises(ValueError):
         svb.dp_utils.vecalign(v.astype(np.float64), v.copy(), [(1, 1)], 0.2, 7, 300, 20000, 100)
+
+
+def test_stream_groups_do_not_change_results(svb, oracle):
+    """Pair groups on separate CUDA streams (engine.BatchRun.run(ngroups)) are a scheduling choice:
+    bit-identical records, and still the oracle's alignments."""
+    from speech_vecalign_b200 import synth
+    shapes = [(220, 230), (640, 600), (90, 100), (301, 322), (700, 650), (33, 30), (410, 400), (150, 170), (820, 800)]
+    a, k = 5, 4
+    types = oracle.alignment_types(a)
+    args = (types, 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    pairs = [synth.synth_pair(n0, n1, k, seed=300 + i) for i, (n0, n1) in enumerate(shapes)]
+    seeds = [40 + i for i in range(len(shapes))]
+    outs = []
+    for streams in (1, 3, 9):
+        outs.append(svb.vecalign_batch([(v0.copy(), v1.copy()) for v0, v1 in pairs], *args, output="records",
+                                       seeds=seeds, streams=streams))
+    for other in outs[1:]:
+        for r0, r1 in zip(outs[0], other):
+            assert np.array_equal(r0["recs"], r1["recs"]) and r0["del_penalty"] == r1["del_penalty"]
+    from speech_vecalign_b200.engine import records_to_alignments
+    for (v0, v1), s, r in zip(pairs, seeds, outs[1]):
+        np.random.seed(s)
+        ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+        al, sc = records_to_alignments(r["recs"])
+        assert same_alignments(al, ref[0]["final_alignments"])
+        assert np.max(np.abs(sc - ref[0]["alignment_scores"])) <= 1e-4
