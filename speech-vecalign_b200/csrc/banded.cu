@@ -3,6 +3,7 @@
 //   svx_banded_costs (dp_core.pyx:165-267 make_sparse_costs)
 //   svx_banded_dp    (dp_core.pyx:269-404 sparse_dp; dp_utils.py:89-143 sparse_traceback +
 //                     process_scores; dp_utils.py:177-275 path glue)
+#include <type_traits>
 #include "svx_common.cuh"
 #include "svx_dp.h"
 
@@ -379,7 +380,14 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     int *bbuf0 = reinterpret_cast<int *>(cbuf1 + cstride);
     int *bbuf1 = bbuf0 + kChunk;
     const double pen = *job.del_penalty;
+    const float *g_costs = job.costs;
+    const int32_t *g_ypath = job.ypath;
+    uint8_t *g_bp = job.bp;
+    double *g_csum = job.csum;
 
+    // chunk c = node diagonals [c*kChunk, (c+1)*kChunk); its cost diagonals (aa - 2) are one
+    // contiguous, 16-byte aligned run in HBM (kChunk*tb and 2*tb floats are multiples of 4 because
+    // the band width is even): copied with 16-byte cp.async, no register staging.
     auto stage = [&](int c, int first_thread, int nthreads) {
         const int start = c * kChunk;
         float *cb = (c & 1) ? cbuf1 : cbuf0;
@@ -387,22 +395,61 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
         const int lo = start - 2, hi = min(start + kChunk, nodes_a) - 2;   // cost diagonals [lo, hi)
         const int clo = max(lo, 0), chi = min(hi, A);
         if (chi > clo) {
-            const float *src = job.costs + (size_t)clo * tb;
+            const float *src = g_costs + (size_t)clo * tb;
             float *dst = cb + (size_t)(clo - lo) * tb;
             const int n = (chi - clo) * tb;
-            for (int i = first_thread; i < n; i += nthreads) dst[i] = __ldg(src + i);
+            const int n4 = n >> 2;
+            for (int i = first_thread; i < n4; i += nthreads) {
+                const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + 4 * i);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(src + 4 * i));
+            }
+            for (int i = 4 * n4 + first_thread; i < n; i += nthreads) dst[i] = __ldg(src + i);
         }
         for (int i = first_thread; i < kChunk; i += nthreads) {
             const int aa = start + i;
-            bb[i] = aa < nodes_a ? svx_boff_out(job.ypath, aa, w) : 0;
+            bb[i] = aa < nodes_a ? svx_boff_out(g_ypath, aa, w) : 0;
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
     };
 
     // ---- phase 1 ------------------------------------------------------------------------------
-    double hist[NH + 1];     // hist[s] = csum of this lane's slot on diagonal aa - s
+    // Lanes >= B always hold +inf, and so do lattice nodes outside the documents, so a predecessor
+    // outside the node band (source lane < 0 wraps to a lane >= B since B + K <= 32 - 1) or with a
+    // negative coordinate contributes +inf and can never win the strict '<': no range tests in the
+    // candidate loop.
+    double hist[NH + 1];     // hist[s] = csum of this lane's slot on diagonal aa - s (s >= 1)
     int bofh[NH + 1];        // bofh[s] = b_offset_out[aa - s]
 #pragma unroll
     for (int s = 0; s <= NH; ++s) { hist[s] = INFINITY; bofh[s] = 0; }
+
+    // best alignment-type candidate of diagonal `aa` (band offset bo_a, staged costs crow) given that
+    // hist[k]/bofh[k] describe diagonal aa - HOFF - k ... i.e. the caller is HOFF diagonals behind.
+    // Two independent strict-'<' chains (first half / second half of the type list) halve the
+    // dependent compare-select latency and keep the reference's first-minimum tie-break.
+    auto type_candidates = [&](auto hoff_tag, int bo_a, const float *crow, double &best_out, int &code_out) {
+        constexpr int HOFF = decltype(hoff_tag)::value;
+        constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
+        double b0 = INFINITY, b1 = INFINITY;
+        int c0 = SVX_BP_NONE, c1 = SVX_BP_NONE;
+        int t = 0;
+#pragma unroll
+        for (int x = 1; x <= K; ++x) {
+#pragma unroll
+            for (int y = 1; x + y <= K + 1; ++y, ++t) {
+                const int s = x + y;                       // >= 2, so s - HOFF >= 1
+                const int src = lane + (bo_a - bofh[s - HOFF]) - y;
+                const double pv = __shfl_sync(0xffffffffu, hist[s - HOFF], src & 31);
+                const double tot = __dadd_rn(pv, (double)crow[t * B]);
+                if (t < SPLIT) { if (tot < b0) { b0 = tot; c0 = t; } }
+                else { if (tot < b1) { b1 = tot; c1 = t; } }
+            }
+        }
+        if (SPLIT < T && b1 < b0) { b0 = b1; c0 = c1; }
+        best_out = b0; code_out = c0;
+    };
+    using Tag0 = std::integral_constant<int, 0>;
+    using Tag1 = std::integral_constant<int, 1>;
 
     const int nchunks = (nodes_a + kChunk - 1) / kChunk;
     stage(0, tid, blockDim.x);
@@ -415,52 +462,46 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             const int *bo = (c & 1) ? bbuf1 : bbuf0;
             const int start = c * kChunk;
             const int end = min(start + kChunk, nodes_a);
-#pragma unroll 2
+            double tbest; int tcode;
+            type_candidates(Tag0{}, bo[0], cb + lane, tbest, tcode);
             for (int aa = start; aa < end; ++aa) {
                 const int bo0 = bo[aa - start];
-                bofh[0] = bo0;
+                // software pipeline: the type candidates of diagonal aa+1 only read diagonals <= aa-1,
+                // so they are issued here, beside the latency chain of diagonal aa
+                double nbest = INFINITY; int ncode = SVX_BP_NONE;
+                if (aa + 1 < end) {
+                    // relative to aa+1 the history is one diagonal behind: bofh[] lacks boff(aa)
+                    const int keep = bofh[0];
+                    bofh[0] = bo0;
+                    type_candidates(Tag1{}, bo[aa + 1 - start], cb + (size_t)(aa + 1 - start) * tb + lane, nbest, ncode);
+                    bofh[0] = keep;
+                }
                 const int yy = lane + bo0, xx = aa - yy;
-                const float *crow = cb + (size_t)(aa - start) * tb + lane;
                 // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the
                 // deletions - reference quirk, dp_core.pyx:382,390)
-                const bool cell_ok = xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && aa - 2 < A;
-                double best = INFINITY;
-                int code = SVX_BP_NONE;
-                int t = 0;
-#pragma unroll
-                for (int x = 1; x <= K; ++x) {
-#pragma unroll
-                    for (int y = 1; x + y <= K + 1; ++y, ++t) {
-                        const int s = x + y;
-                        const int src = lane + (bo0 - bofh[s]) - y;
-                        const double pv = __shfl_sync(0xffffffffu, hist[s], src & 31);
-                        const double tot = __dadd_rn(pv, (double)crow[t * B]);
-                        const bool ok = cell_ok && xx >= x && yy >= y && src >= 0 && src < B;
-                        if (ok && tot < best) { best = tot; code = t; }
-                    }
-                }
+                const bool cell_ok = lane < B && xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && aa - 2 < A;
+                double best = tbest;
+                int code = tcode;
                 {
                     const double hp = __dadd_rn(hist[1], pen);
                     const int d1 = bo0 - bofh[1];
-                    int src = lane + d1 - 1;                                   // (0,1): consume y
-                    double tot = __shfl_sync(0xffffffffu, hp, src & 31);
-                    bool ok = cell_ok && yy >= 1 && src >= 0 && src < B;
-                    if (ok && tot < best) { best = tot; code = T; }
-                    src = lane + d1;                                           // (1,0): consume x
-                    tot = __shfl_sync(0xffffffffu, hp, src & 31);
-                    ok = cell_ok && xx >= 1 && src >= 0 && src < B;
-                    if (ok && tot < best) { best = tot; code = T + 1; }
+                    double tot = __shfl_sync(0xffffffffu, hp, (lane + d1 - 1) & 31);     // (0,1): consume y
+                    if (tot < best) { best = tot; code = T; }
+                    tot = __shfl_sync(0xffffffffu, hp, (lane + d1) & 31);                // (1,0): consume x
+                    if (tot < best) { best = tot; code = T + 1; }
                 }
-                if (xx == 0 && yy >= 0 && yy <= s1) { best = __dmul_rn(pen, (double)yy); code = T; }
-                else if (yy == 0 && xx >= 0 && xx <= s0) { best = __dmul_rn(pen, (double)xx); code = T + 1; }
+                if (!cell_ok) { best = INFINITY; code = SVX_BP_NONE; }
                 if (lane < B) {
-                    job.bp[(size_t)aa * B + lane] = (uint8_t)code;
-                    job.csum[(size_t)aa * B + lane] = best;
+                    if (xx == 0 && yy >= 0 && yy <= s1) { best = __dmul_rn(pen, (double)yy); code = T; }
+                    else if (yy == 0 && xx >= 0 && xx <= s0) { best = __dmul_rn(pen, (double)xx); code = T + 1; }
+                    g_bp[(size_t)aa * B + lane] = (uint8_t)code;
+                    g_csum[(size_t)aa * B + lane] = best;
                 }
 #pragma unroll
                 for (int s = NH; s >= 2; --s) { hist[s] = hist[s - 1]; bofh[s] = bofh[s - 1]; }
                 hist[1] = best;
                 bofh[1] = bo0;
+                tbest = nbest; tcode = ncode;
             }
         }
         __syncthreads();
@@ -717,6 +758,7 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
         else K = kk;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (standard && bmax + K > 32) standard = false;     // source-lane wrap-around must land on a lane >= band
     if (standard) {
         switch (K) {
 #define CASE(KK) case KK: return launch_dp_tri<KK>(jobs_d, njobs, bmax, alen_max, st);
