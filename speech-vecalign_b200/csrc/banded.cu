@@ -25,14 +25,14 @@ namespace {
 //   TRI  = false: any type list; passes over CX x CY blocks of (x overlap, y overlap) with a
 //                 lookup table (kx,ky) -> type index.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBC = 64;         // floats of the embedding dimension per staged slice
-constexpr int kBS = kBC + 4;    // padded row stride (68 floats = 17 x 16 B: conflict-free LDS.128)
+constexpr int kBC = 32;         // floats of the embedding dimension per staged slice (128 B per row)
+constexpr int kBS = kBC + 4;    // padded row stride (36 floats = 9 x 16 B: conflict-free LDS.128)
 
 template <int CX, int CY, bool TRI, bool EXACT>
 __global__ void __launch_bounds__(384)
-k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
+k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
 {
-    extern __shared__ __align__(16) float tile[];
+    extern __shared__ __align__(16) float tile[];  // two slice buffers of nrows_max * kBS floats
     __shared__ int16_t tmap[TRI ? 1 : 64 * 64];   // (kx,ky) -> type index, generic path only
     const SvxBandJob &job = jobs[blockIdx.y];
     const int a0 = blockIdx.x * ta;
@@ -45,10 +45,13 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
     const int ylo = boff_first, yhi = boff_last + B - 1;
     const int xlo = a0 - boff_first - B + 1, xhi = (a0 + na - 1) - boff_last;
     const int NX = xhi - xlo + 1, NY = yhi - ylo + 1;
+    const int buf_floats = (ta + 2 * B - 1) * (CX > CY ? CX : CY) * kBS;
 
     const int tid = threadIdx.x;
-    const bool has_cell = tid < na * B;
-    const int la = has_cell ? tid / B : 0, b = has_cell ? tid % B : 0;
+    // lb = band width rounded up to a multiple of 8 lanes: a quarter-warp (one LDS.128 phase) then
+    // never straddles two anti-diagonals, so its 8 lanes read 8 consecutive rows = 8 bank groups
+    const bool has_cell = tid / lb < na && tid % lb < B;
+    const int la = has_cell ? tid / lb : 0, b = has_cell ? tid % lb : 0;
     const int a = a0 + la;
     const int yy = job.ypath[a] - w + b;
     const int xx = a - yy;
@@ -77,9 +80,11 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
                 for (int j = 0; j < CY; ++j) acc[i][j] = 0.0f;
 
             const int xrows = CX * NX, nrows = xrows + CY * NY;
-            for (int sl = 0; sl < slices; ++sl) {
+            // slice `sl` of every touched row -> buffer sl & 1, 16 bytes per cp.async, zero-filled for
+            // rows outside the documents / overlaps (src-size 0)
+            auto issue = [&](int sl) {
+                float *buf = tile + (sl & 1) * buf_floats;
                 const int d0 = sl * kBC;
-                __syncthreads();
                 for (int f = tid; f < nrows * (kBC / 4); f += blockDim.x) {
                     const int row = f / (kBC / 4), c4 = f % (kBC / 4);
                     const float *src = nullptr;
@@ -91,21 +96,34 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
                         const int k = ky0 + r2 / NY, seg = ylo + r2 % NY;
                         if (k < job.k1 && seg >= 0 && seg < s1) src = job.v1 + ((size_t)k * s1 + seg) * dim;
                     }
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (src) v = ldg_f4(src + d0 + 4 * c4);
-                    *reinterpret_cast<float4 *>(tile + (size_t)row * kBS + 4 * c4) = v;
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)row * kBS + 4 * c4);
+                    const float *gp = src ? src + d0 + 4 * c4 : job.v0;
+                    const int nbytes = src ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(nbytes));
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+            };
+            __syncthreads();              // previous (kx0, ky0) pass is done with both buffers
+            issue(0);
+            for (int sl = 0; sl < slices; ++sl) {
+                if (sl + 1 < slices) {
+                    issue(sl + 1);        // lands while slice sl is being consumed
+                    asm volatile("cp.async.wait_group 1;\n" ::);
+                } else {
+                    asm volatile("cp.async.wait_group 0;\n" ::);
                 }
                 __syncthreads();
+                const float *buf = tile + (sl & 1) * buf_floats;
                 if (inside) {
 #pragma unroll 2
                     for (int d = 0; d < kBC; d += 4) {
                         float4 xv[CX], yv[CY];
 #pragma unroll
                         for (int i = 0; i < CX; ++i)
-                            xv[i] = *reinterpret_cast<const float4 *>(tile + (size_t)(i * NX + xr) * kBS + d);
+                            xv[i] = *reinterpret_cast<const float4 *>(buf + (size_t)(i * NX + xr) * kBS + d);
 #pragma unroll
                         for (int j = 0; j < CY; ++j)
-                            yv[j] = *reinterpret_cast<const float4 *>(tile + (size_t)(xrows + j * NY + yr) * kBS + d);
+                            yv[j] = *reinterpret_cast<const float4 *>(buf + (size_t)(xrows + j * NY + yr) * kBS + d);
 #pragma unroll
                         for (int i = 0; i < CX; ++i)
 #pragma unroll
@@ -125,6 +143,7 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta)
                             }
                     }
                 }
+                __syncthreads();          // buffer sl & 1 is free for slice sl + 2
             }
             if (has_cell) {
                 float *out = job.costs + (size_t)a * T * B + b;
@@ -636,21 +655,22 @@ inline bool is_standard_types(const SvxBandJob &j, int *k_out)
 template <int CX, int CY, bool TRI>
 int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, cudaStream_t st)
 {
-    const int ta = 384 / band < 16 ? 384 / band : 16;   // <= 384 threads: up to 170 registers each
+    const int lb = (band + 7) & ~7;
+    const int ta = 384 / lb < 16 ? 384 / lb : 16;       // <= 384 threads: up to 170 registers each
     if (ta < 1) return -1;
-    int threads = ((ta * band + 31) / 32) * 32;
+    int threads = ta * lb;
     const int maxk = CX > CY ? CX : CY;
-    const size_t smem = (size_t)maxk * (ta + 2 * band - 1) * kBS * sizeof(float);
+    const size_t smem = (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float);   // two slice buffers
     if (smem > 220 * 1024) return -1;
     dim3 grid((max_alen + ta - 1) / ta, nj);
     if (mode == SVX_COST_EXACT) {
         auto kern = k_banded_costs<CX, CY, TRI, true>;
         if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta, lb);
     } else {
         auto kern = k_banded_costs<CX, CY, TRI, false>;
         if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta, lb);
     }
     SVX_LAUNCH_CHECK();
     return SVX_OK;
@@ -729,7 +749,7 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
     const size_t walk_bytes = (size_t)win * per_diag + 16;
     const size_t smem = dp_bytes > walk_bytes ? dp_bytes : walk_bytes;
     auto kern = k_banded_dp_tri<K>;
-    if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<njobs, 128, smem, st>>>(jobs_d, chunk, win);
     SVX_LAUNCH_CHECK();
     return SVX_OK;
@@ -758,8 +778,7 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
         else K = kk;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (standard && bmax + K > 32) standard = false;     // source-lane wrap-around must land on a lane >= band
-    if (standard) {
+    if (standard && bmax + K <= 32) {      // source-lane wrap-around must land on a lane >= band
         switch (K) {
 #define CASE(KK) case KK: return launch_dp_tri<KK>(jobs_d, njobs, bmax, alen_max, st);
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
