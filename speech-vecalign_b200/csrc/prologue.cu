@@ -249,41 +249,75 @@ __global__ void __launch_bounds__(512) k_sort_samples(const SvxScoreJob *jobs)
     for (int i = tid; i < n; i += blockDim.x) job.perm[atomicAdd(&cnt[job.xi[i]], 1)] = i;
 }
 
+// A warp scores 32 samples.  Each lane must consume its own two rows in increasing d (the
+// reference's summation order), but 32 lanes streaming 32 different rows would cost one L1 tag
+// look-up per lane and 16 bytes: instead the warp fetches every 128-byte row piece with 8 lanes
+// (coalesced LDG.128, 4 rows per instruction), parks the 32 x 32-float block in shared memory
+// (row stride 36 floats: conflict-free for the store and for the per-lane LDS.128 read-back) and each
+// lane then reads its own row back.
+constexpr int kScWarps = 4;
+constexpr int kScStride = 36;
+
 template <bool EXACT>
-__global__ void __launch_bounds__(128) k_score_pairs(const SvxScoreJob *jobs, int dim)
+__global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob *jobs, int dim)
 {
+    __shared__ __align__(16) float sx[kScWarps][32 * kScStride];
+    __shared__ __align__(16) float sy[kScWarps][32 * kScStride];
     const SvxScoreJob job = jobs[blockIdx.y];
-    int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= job.nsamp) return;
-    int xi, yi;
-    if (job.xi) {
-        if (job.perm && !job.dots && job.ne <= kSortMaxRows) i = job.perm[i];
-        xi = job.xi[i]; yi = job.yi[i];
-    } else { xi = i / job.nf; yi = i % job.nf; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int base = (blockIdx.x * kScWarps + warp) * 32;
+    if (base >= job.nsamp) return;                       // warp-uniform
+    int i = base + lane;
+    const bool valid = i < job.nsamp;
+    int xi = 0, yi = 0;
+    if (valid) {
+        if (job.xi) {
+            if (job.perm && !job.dots && job.ne <= kSortMaxRows) i = job.perm[i];
+            xi = job.xi[i]; yi = job.yi[i];
+        } else { xi = i / job.nf; yi = i % job.nf; }
+    }
     float dot = 0.0f;
     if (job.dots) {
-        dot = job.dots[(size_t)xi * job.nf + yi];
+        if (valid) dot = job.dots[(size_t)xi * job.nf + yi];
     } else {
-        const float *a = job.e + (size_t)xi * dim;
-        const float *b = job.f + (size_t)yi * dim;
-#pragma unroll 2
-        for (int d = 0; d < dim; d += 8) {
-            const float4 a0 = ldg_f4(a + d), a1 = ldg_f4(a + d + 4);
-            const float4 b0 = ldg_f4(b + d), b1 = ldg_f4(b + d + 4);
-            if (EXACT) {
-                dot = __fadd_rn(dot, __fmul_rn(a0.x, b0.x)); dot = __fadd_rn(dot, __fmul_rn(a0.y, b0.y));
-                dot = __fadd_rn(dot, __fmul_rn(a0.z, b0.z)); dot = __fadd_rn(dot, __fmul_rn(a0.w, b0.w));
-                dot = __fadd_rn(dot, __fmul_rn(a1.x, b1.x)); dot = __fadd_rn(dot, __fmul_rn(a1.y, b1.y));
-                dot = __fadd_rn(dot, __fmul_rn(a1.z, b1.z)); dot = __fadd_rn(dot, __fmul_rn(a1.w, b1.w));
-            } else {
-                dot = fmaf(a0.x, b0.x, dot); dot = fmaf(a0.y, b0.y, dot);
-                dot = fmaf(a0.z, b0.z, dot); dot = fmaf(a0.w, b0.w, dot);
-                dot = fmaf(a1.x, b1.x, dot); dot = fmaf(a1.y, b1.y, dot);
-                dot = fmaf(a1.z, b1.z, dot); dot = fmaf(a1.w, b1.w, dot);
+        // rows fetched by this lane in load step g: sample 4g + lane/8, 16-byte piece lane%8
+        const int sub = lane >> 3, piece = 4 * (lane & 7);
+        int xr[8], yr[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            xr[g] = __shfl_sync(0xffffffffu, xi, 4 * g + sub);
+            yr[g] = __shfl_sync(0xffffffffu, yi, 4 * g + sub);
+        }
+        float *mx = sx[warp], *my = sy[warp];
+        for (int d0 = 0; d0 < dim; d0 += 32) {
+            float4 vx[8], vy[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                vx[g] = ldg_f4(job.e + (size_t)xr[g] * dim + d0 + piece);
+                vy[g] = ldg_f4(job.f + (size_t)yr[g] * dim + d0 + piece);
             }
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                *reinterpret_cast<float4 *>(mx + (4 * g + sub) * kScStride + piece) = vx[g];
+                *reinterpret_cast<float4 *>(my + (4 * g + sub) * kScStride + piece) = vy[g];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(mx + lane * kScStride + 4 * q);
+                const float4 b = *reinterpret_cast<const float4 *>(my + lane * kScStride + 4 * q);
+                if (EXACT) {
+                    dot = __fadd_rn(dot, __fmul_rn(a.x, b.x)); dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
+                    dot = __fadd_rn(dot, __fmul_rn(a.z, b.z)); dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
+                } else {
+                    dot = fmaf(a.x, b.x, dot); dot = fmaf(a.y, b.y, dot);
+                    dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
+                }
+            }
+            __syncwarp();
         }
     }
-    job.scores[i] = svx_pair_score(dot, job.norm_e[xi], job.norm_f[yi]);
+    if (valid) job.scores[i] = svx_pair_score(dot, job.norm_e[xi], job.norm_f[yi]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -413,7 +447,7 @@ extern "C" int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs
 extern "C" int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *jobs_h, int njobs, int dim, int mode,
                                void *stream)
 {
-    SVX_REQUIRE(dim > 0 && dim % 8 == 0, SVX_ERR_UNSUPPORTED, "svx_score_pairs: dim %d must be a multiple of 8", dim);
+    SVX_REQUIRE(dim > 0 && dim % 32 == 0, SVX_ERR_UNSUPPORTED, "svx_score_pairs: dim %d must be a multiple of 32", dim);
     if (njobs <= 0) return SVX_OK;
     cudaStream_t st = (cudaStream_t)stream;
     int sort_rows = 0;
@@ -434,8 +468,8 @@ extern "C" int svx_score_pairs(const SvxScoreJob *jobs_d, const SvxScoreJob *job
         for (int j = 0; j < nj; ++j) ms = jobs_h[j0 + j].nsamp > ms ? jobs_h[j0 + j].nsamp : ms;
         if (ms == 0) continue;
         dim3 grid((ms + 127) / 128, nj);
-        if (mode == SVX_COST_EXACT) k_score_pairs<true><<<grid, 128, 0, st>>>(jobs_d + j0, dim);
-        else k_score_pairs<false><<<grid, 128, 0, st>>>(jobs_d + j0, dim);
+        if (mode == SVX_COST_EXACT) k_score_pairs<true><<<grid, kScWarps * 32, 0, st>>>(jobs_d + j0, dim);
+        else k_score_pairs<false><<<grid, kScWarps * 32, 0, st>>>(jobs_d + j0, dim);
         SVX_LAUNCH_CHECK();
     }
     return SVX_OK;
