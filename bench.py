@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="document pairs per GPU per step (0 = workload default)")
-    ap.add_argument("--cost-mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--cost-mode", default="exact", choices=["exact", "fast", "tc"])
     ap.add_argument("--streams", type=int, default=4, help="pair groups run on separate CUDA streams (1 = serial chain)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -237,7 +237,7 @@ def run_ours(args):
     k = a - 1
     types = svb.make_alignment_types(a)
     w = math.ceil(k / 2) + PARAMS["search_buffer_size"]
-    mode = capi.SVX_COST_EXACT if args.cost_mode == "exact" else capi.SVX_COST_FAST
+    mode = {"exact": capi.SVX_COST_EXACT, "fast": capi.SVX_COST_FAST, "tc": capi.SVX_COST_TC}[args.cost_mode]
 
     # ---- synthetic inputs born in HBM: a pristine copy and the working copy the path mutates ----
     off0 = np.concatenate([[0], np.cumsum(k * (n0 + n1) * DIM)]).astype(np.int64)

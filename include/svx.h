@@ -17,7 +17,8 @@
  *   - All fp32 dot products of the cost kernels are evaluated in the reference's order
  *     (sequential multiply-then-add over the embedding dimension, no FMA) when mode ==
  *     SVX_COST_EXACT, so costs are bit-identical to dp_core.pyx given identical inputs;
- *     SVX_COST_FAST contracts to FMA (same order) and is within 2e-6 absolute.
+ *     SVX_COST_FAST contracts to FMA (same order) and is within 2e-6 absolute; SVX_COST_TC
+ *     additionally computes the coarsest-level matrix as a 3xTF32 tensor-core GEMM (4e-6).
  *
  * Each entry point cites the reference interface it replaces (file:line under /root/reference).
  */
@@ -47,6 +48,8 @@ extern "C" {
 /* cost arithmetic */
 #define SVX_COST_EXACT 0
 #define SVX_COST_FAST 1
+#define SVX_COST_TC 2         /* FAST + the coarsest-level cost matrix on tcgen05 tensor cores
+                                 (3xTF32, TMA-fed); needs SvxDenseJob.tmap0/tmap1              */
 
 /* per-job device status bits (status_d) */
 #define SVX_ST_OK 0
@@ -142,6 +145,9 @@ typedef struct SvxDenseJob {
     const float *n1;           /* (s1)                                                   */
     float *costs;              /* (s0, s1) output of svx_dense_costs                     */
     float *dots;               /* (s0, s1) or NULL: the raw dot products v0[x].v1[y]     */
+    const void *tmap0;         /* device copies (64-byte aligned, 128 B each) of the TMA */
+    const void *tmap1;         /*   descriptors of v0 / v1 (svx_dense_tmaps_encode); only */
+                               /*   read when mode == SVX_COST_TC                         */
     const double *del_penalty; /* (1); narrowed to fp32 as dense_dp(float pen) does      */
     uint8_t *bp;               /* (s0+1, s1+1) backpointers 0/1/2, 4 at the origin       */
     double *csum;              /* (s0+1, s1+1) or NULL (debug/parity only)               */
@@ -156,6 +162,10 @@ typedef struct SvxDenseJob {
 SVX_API int svx_dense_costs(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, int mode,
                     void *stream);
 SVX_API int svx_dense_dp(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, void *stream);
+/* Host only: encodes the two CUtensorMap descriptors (128 B each; rows x dim fp32, 128-row x 32-float
+ * boxes, 128-byte swizzle) of every job's v0 / v1 into out_host[2*j], out_host[2*j+1].  The caller
+ * copies them to the device and sets tmap0 / tmap1 before calling svx_dense_costs(SVX_COST_TC). */
+SVX_API int svx_dense_tmaps_encode(const SvxDenseJob *jobs_h, int njobs, int dim, void *out_host);
 
 /* Length of the search path built from a coarse alignment of (c0,c1) segments for a target level
  * of (t0,t1) segments (upsample=1), or from a same-size dense alignment (upsample=0). */

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvx.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-SVX_COST_EXACT, SVX_COST_FAST = 0, 1
+SVX_COST_EXACT, SVX_COST_FAST, SVX_COST_TC = 0, 1, 2
 SVX_ST_LEFT_BAND, SVX_ST_NO_BACKPTR, SVX_ST_OVERFLOW = 1, 2, 4
 SVX_BP_NONE = 255
 SVX_MAX_TYPES = 126
@@ -31,7 +31,7 @@ NORM = np.dtype([("vecs", _P), ("other", _P), ("idx", _P), ("mbar", _P), ("norms
 SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
                   ("scores", _P), ("del_penalty", _P), ("perm", _P), ("dots", _P),
                   ("ne", np.int32), ("nf", np.int32), ("nsamp", np.int32)], align=True)
-DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("dots", _P), ("del_penalty", _P),
+DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("dots", _P), ("tmap0", _P), ("tmap1", _P), ("del_penalty", _P),
                   ("bp", _P), ("csum", _P), ("ypath", _P), ("status_d", _P),
                   ("s0", np.int32), ("s1", np.int32), ("t0", np.int32), ("t1", np.int32),
                   ("upsample", np.int32), ("path_len", np.int32)], align=True)
@@ -85,6 +85,7 @@ def lib():
         "svx_host_del_knob": [vp, ci, cd, vp],
         "svx_dense_costs": [vp, vp, ci, ci, ci, vp],
         "svx_dense_dp": [vp, vp, ci, vp],
+        "svx_dense_tmaps_encode": [vp, ci, ci, vp],
         "svx_path_len": [ci, ci, ci, ci, ci],
         "svx_banded_costs": [vp, vp, ci, ci, ci, vp],
         "svx_banded_dp": [vp, vp, ci, vp],
@@ -111,7 +112,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_score_pairs", "svx_del_knob",
-    "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_path_len", "svx_banded_costs",
+    "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_dense_tmaps_encode", "svx_path_len", "svx_banded_costs",
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_version",
     "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
 ]

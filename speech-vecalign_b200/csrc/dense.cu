@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(256) k_dense_dp(const SvxDenseJob *jobs)
 
 }  // namespace
 
+int svx_dense_costs_tc_launch(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, cudaStream_t st);
+
 extern "C" int svx_dense_costs(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, int mode,
                                void *stream)
 {
+    if (mode == SVX_COST_TC) return njobs > 0 ? svx_dense_costs_tc_launch(jobs_d, jobs_h, njobs, dim, (cudaStream_t)stream) : SVX_OK;
     SVX_REQUIRE(dim > 0 && dim % kDC == 0, SVX_ERR_UNSUPPORTED, "svx_dense_costs: dim %d must be a multiple of %d", dim, kDC);
     if (njobs <= 0) return SVX_OK;
     cudaStream_t st = (cudaStream_t)stream;

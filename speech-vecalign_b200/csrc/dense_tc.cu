@@ -1,0 +1,300 @@
+// dense_tc.cu — coarsest-level cost matrix on the 5th-generation tensor cores (sm_100a):
+//   svx_dense_costs(mode = SVX_COST_TC)   (dp_core.pyx:36-77 make_dense_costs)
+//
+// costs[x, y] = 2 (1 - v0[x].v1[y]) / (1e-6 + n0[x] + n1[y]) is a true dense (s0 x 1024) . (1024 x s1)
+// contraction per document pair.  One CTA computes one 128 x 128 tile of one pair:
+//
+//   TMA      cp.async.bulk.tensor.2d loads 128 rows x 32 floats (128 B, SWIZZLE_128B) of each operand
+//            per k-slice into a 3-stage shared-memory ring, completion on an mbarrier; rows past the
+//            end of a document are zero-filled by the TMA unit.  One CUtensorMap per operand per
+//            pair, encoded on the host (svx_dense_tmaps_encode) and shipped with the job descriptors.
+//   split    all four warps split each fp32 operand element into hi = its upper 19 bits (exactly a
+//            TF32 number, written back in place) and lo = a - hi (written to a second buffer with the
+//            same swizzled addressing), then fence.proxy.async so the tensor core sees the writes.
+//   tcgen05  one elected thread issues, per 8-wide k step, three kind::tf32 MMAs (hi.hi, hi.lo,
+//            lo.hi; the lo.lo term is < 2^-22 relative) accumulating the 128 x 128 fp32 tile in TMEM
+//            (128 columns), and commits to an mbarrier that releases the ring stage back to TMA.
+//   epilogue tcgen05.ld 32x32b brings each warp's 32 accumulator rows to registers; the cost formula
+//            is evaluated in double exactly as in the reference and stored with the raw dots.
+//
+// 3xTF32 tolerance (tests/test_gpu_tensor_core.py): |dot - fp32 sequential dot| <= 4e-6 on unit
+// vectors, i.e. costs within 1e-5 absolute; the coarse alignment path is checked to stay identical.
+#include <string.h>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "svx_common.cuh"
+
+namespace {
+
+constexpr int kTM = 128;             // tile rows (x), UMMA M
+constexpr int kTN = 128;             // tile cols (y), UMMA N
+constexpr int kTK = 32;              // floats per k-slice = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kTileBytes = kTM * kTK * 4;          // 16 KB per operand per stage
+constexpr int kStageBytes = 4 * kTileBytes;        // A hi, B hi, A lo, B lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */;
+constexpr int kTmemCols = 512;          // three 128-column fp32 accumulators (allocation must be a power of 2)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, unsigned bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO = 64 x 16 B),
+// LBO is 1 for swizzled K-major layouts, descriptor version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc(unsigned smem_addr)
+{
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t da, uint64_t db, unsigned accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kInstrDesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void split_tf32(float4 &v, float4 &lo)
+{
+    float4 hi;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    lo.x = __fsub_rn(v.x, hi.x); lo.y = __fsub_rn(v.y, hi.y);
+    lo.z = __fsub_rn(v.z, hi.z); lo.w = __fsub_rn(v.w, hi.w);
+    v = hi;
+}
+
+__global__ void __launch_bounds__(128, 1) k_dense_costs_tc(const SvxDenseJob *jobs, int dim)
+{
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) unsigned long long bars[2 * kStages + 1];   // full[], free[], accumulator done
+    __shared__ unsigned tmem_slot;
+    const SvxDenseJob job = jobs[blockIdx.z];
+    const int x0 = blockIdx.y * kTM, y0 = blockIdx.x * kTN;
+    if (x0 >= job.s0 || y0 >= job.s1) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    const unsigned tiles_u32 = smem_u32(tiles);
+    const unsigned bar_full = smem_u32(&bars[0]), bar_free = smem_u32(&bars[kStages]), bar_acc = smem_u32(&bars[2 * kStages]);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_free + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+    const unsigned tmem_d = tmem_slot;
+
+    const int nk = dim / kTK;
+    auto issue_tma = [&](int ks) {
+        const int s = ks % kStages;
+        const unsigned base = tiles_u32 + s * kStageBytes;
+        mbar_expect_tx(bar_full + 8 * s, 2 * kTileBytes);
+        tma_load_2d(base, job.tmap0, bar_full + 8 * s, ks * kTK, x0);
+        tma_load_2d(base + kTileBytes, job.tmap1, bar_full + 8 * s, ks * kTK, y0);
+    };
+    if (tid == 0)
+        for (int ks = 0; ks < kStages && ks < nk; ++ks) issue_tma(ks);
+
+    for (int ks = 0; ks < nk; ++ks) {
+        const int s = ks % kStages;
+        const unsigned ph = (ks / kStages) & 1;
+        mbar_wait(bar_full + 8 * s, ph);                       // both operand slices have landed
+        // hi/lo split, elementwise: the swizzled position of an element is the same in all four tiles
+        float4 *hi4 = reinterpret_cast<float4 *>(tiles + (size_t)s * kStageBytes);
+        float4 *lo4 = hi4 + 2 * kTileBytes / 16;
+#pragma unroll 4
+        for (int i = tid; i < 2 * kTileBytes / 16; i += 128) {
+            float4 v = hi4[i], lo;
+            split_tf32(v, lo);
+            hi4[i] = v;
+            lo4[i] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            const unsigned base = tiles_u32 + s * kStageBytes;
+            const unsigned a_hi = base, b_hi = base + kTileBytes, a_lo = base + 2 * kTileBytes, b_lo = base + 3 * kTileBytes;
+#pragma unroll
+            // The tensor core rounds toward zero each time it adds an MMA result into the fp32
+            // accumulator, so the error grows with the number of MMAs per accumulator.  The hi.hi
+            // products alternate between two accumulators (even / odd k-slices) and the two small
+            // cross terms (2^-11 of the main term) go to a third one; the epilogue adds the three.
+            const unsigned d_main = tmem_d + (unsigned)((ks & 1) * kTN);
+            const unsigned d_cross = tmem_d + (unsigned)(2 * kTN);
+            for (int k = 0; k < kTK / 8; ++k) {                // UMMA K = 8 tf32 = 32 bytes along the row
+                const unsigned off = k * 32;
+                umma_tf32(d_main, umma_desc(a_hi + off), umma_desc(b_hi + off), (ks >= 2) || k != 0);
+                umma_tf32(d_cross, umma_desc(a_hi + off), umma_desc(b_lo + off), (ks | k) != 0);
+                umma_tf32(d_cross, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+            }
+            umma_commit(bar_free + 8 * s);                     // arrives when these MMAs have read the stage
+            if (ks == nk - 1) umma_commit(bar_acc);
+            // refill the stage consumed one iteration ago (its MMAs have had a whole iteration to drain)
+            const int kr = ks - 1 + kStages;
+            if (ks >= 1 && kr < nk) {
+                const int sr = (ks - 1) % kStages;
+                mbar_wait(bar_free + 8 * sr, ((ks - 1) / kStages) & 1);
+                issue_tma(kr);
+            }
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> cost formula -> HBM -----------------------------------------
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+    const int x = x0 + warp * 32 + lane;                       // warp w owns TMEM lanes [32w, 32w + 32)
+    const float nx = x < job.s0 ? job.n0[x] : 1.0f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kTN; c0 += 32) {
+        float dot[32];
+#pragma unroll
+        for (int acc = 0; acc < 3; ++acc) {
+            if (acc == 1 && nk < 2) continue;                 // odd-slice accumulator never written
+            uint32_t r[32];
+            const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16) + (unsigned)(acc * kTN + c0);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dot[j] = acc == 0 ? __uint_as_float(r[j]) : __fadd_rn(dot[j], __uint_as_float(r[j]));
+        }
+        if (x < job.s0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int y = y0 + c0 + j;
+                if (y < job.s1) {
+                    job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(dot[j], nx, job.n1[y]);
+                    if (job.dots) job.dots[(size_t)x * job.s1 + y] = dot[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols));
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+}  // namespace
+
+// Host: one CUtensorMap (128 B) per operand per job -> out_host[2*j], out_host[2*j+1].  The caller
+// copies them to the device and points SvxDenseJob.tmap0 / tmap1 at the copies (64-byte aligned).
+extern "C" int svx_dense_tmaps_encode(const SvxDenseJob *jobs_h, int njobs, int dim, void *out_host)
+{
+    SVX_REQUIRE(dim > 0 && dim % kTK == 0, SVX_ERR_UNSUPPORTED, "svx_dense_tmaps_encode: dim %d must be a multiple of %d", dim, kTK);
+    SVX_REQUIRE(out_host || njobs <= 0, SVX_ERR_ARG, "svx_dense_tmaps_encode: null output");
+    auto enc = encode_fn();
+    SVX_REQUIRE(enc, SVX_ERR_CUDA, "svx_dense_tmaps_encode: cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap *out = reinterpret_cast<CUtensorMap *>(out_host);
+    for (int j = 0; j < njobs; ++j) {
+        for (int side = 0; side < 2; ++side) {
+            const float *base = side ? jobs_h[j].v1 : jobs_h[j].v0;
+            const int rows = side ? jobs_h[j].s1 : jobs_h[j].s0;
+            CUtensorMap *m = out + 2 * j + side;
+            memset(m, 0, sizeof(*m));
+            if (rows <= 0 || !base) continue;
+            SVX_REQUIRE(((uintptr_t)base & 15) == 0, SVX_ERR_ARG, "svx_dense_tmaps_encode: operand of job %d is not 16-byte aligned", j);
+            cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+            cuuint64_t gstride[1] = {(cuuint64_t)dim * sizeof(float)};
+            cuuint32_t box[2] = {(cuuint32_t)kTK, (cuuint32_t)kTM};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SVX_REQUIRE(r == CUDA_SUCCESS, SVX_ERR_CUDA, "svx_dense_tmaps_encode: cuTensorMapEncodeTiled failed (%d) for job %d", (int)r, j);
+        }
+    }
+    return SVX_OK;
+}
+
+int svx_dense_costs_tc_launch(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, cudaStream_t st)
+{
+    SVX_REQUIRE(dim > 0 && dim % kTK == 0, SVX_ERR_UNSUPPORTED, "svx_dense_costs: dim %d must be a multiple of %d", dim, kTK);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SVX_CUDA_OK(cudaFuncSetAttribute(k_dense_costs_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int m0 = 0, m1 = 0;
+        for (int j = 0; j < nj; ++j) {
+            const SvxDenseJob &jb = jobs_h[j0 + j];
+            SVX_REQUIRE(jb.s0 == 0 || jb.s1 == 0 || (jb.tmap0 && jb.tmap1), SVX_ERR_ARG,
+                        "svx_dense_costs: tensor-core mode needs SvxDenseJob.tmap0/tmap1 (svx_dense_tmaps_encode)");
+            if (jb.s0 > 0 && jb.s1 > 0) { m0 = jb.s0 > m0 ? jb.s0 : m0; m1 = jb.s1 > m1 ? jb.s1 : m1; }
+        }
+        if (m0 == 0 || m1 == 0) continue;
+        dim3 grid((m1 + kTN - 1) / kTN, (m0 + kTM - 1) / kTM, nj);
+        SVX_REQUIRE(grid.y <= 65535, SVX_ERR_UNSUPPORTED, "svx_dense_costs: s0 %d too large", m0);
+        k_dense_costs_tc<<<grid, 128, kSmemBytes, st>>>(jobs_d + j0, dim);
+        SVX_LAUNCH_CHECK();
+    }
+    return SVX_OK;
+}

@@ -7,7 +7,8 @@ reference signature and returns the reference's ``stack`` (dp_utils.py:381-390, 
 (vecalign.py:279,292).  All arithmetic runs on the GPU through libsvx.so; there is no CPU path.
 
 Additions: ``vecalign_batch`` (many pairs per call), ``debug=True`` to fill every other stack key
-for parity work, ``cost_mode`` ('exact' | 'fast').
+for parity work, ``cost_mode`` ('exact' | 'fast' | 'tc': fast + the coarsest-level cost matrix
+as a 3xTF32 tcgen05 GEMM).
 
 Semantics kept from the reference: the global ``np.random`` stream is consumed in the reference's
 order; ``width_over2 < 3`` is raised to 3 (:391-393); torch CUDA inputs are normalised in place
@@ -24,7 +25,7 @@ from .engine import BatchRun, records_to_alignments
 
 logger = logging.getLogger('vecalign')
 
-_MODES = {"exact": capi.SVX_COST_EXACT, "fast": capi.SVX_COST_FAST}
+_MODES = {"exact": capi.SVX_COST_EXACT, "fast": capi.SVX_COST_FAST, "tc": capi.SVX_COST_TC}
 
 
 def _device():

@@ -195,6 +195,8 @@ class BatchRun:
         o["xi"] = ar.take(np.where(has_draw, nsamp * 4, 0))
         o["yi"] = ar.take(np.where(has_draw, nsamp * 4, 0))
         o["delpen"] = ar.take(np.full(R, 8))
+        # TMA descriptors of the coarsest level's operands (tensor-core mode), encoded on the host
+        o["tmaps"] = ar.take(np.where(is_top & (cost_mode == capi.SVX_COST_TC), 256, 0))
         # every job descriptor of the batch (upper bound incl. 16-byte alignment slack per array)
         jobs_bytes = (2 * P * capi.ROWS.itemsize + 2 * R * capi.DOWN.itemsize + 2 * R * capi.NORM.itemsize +
                       R * capi.SCORE.itemsize + P * capi.DENSE.itemsize + R * capi.BAND.itemsize + 4096)
@@ -316,6 +318,13 @@ class BatchRun:
         dj["status_d"] = ptr("status")[top] + np.uint64(4)
         dj["s0"], dj["s1"], dj["t0"], dj["t1"] = rs0[top], rs1[top], rs0[tgt], rs1[tgt]
         dj["upsample"], dj["path_len"] = (self.depth > 0), A[tgt]
+        if cost_mode == capi.SVX_COST_TC and P:
+            dj["tmap0"] = ptr("tmaps")[top]
+            dj["tmap1"] = ptr("tmaps")[top] + np.uint64(128)
+            blobs = np.zeros((P, 2, 128), dtype=np.uint8)
+            capi.check(capi.lib().svx_dense_tmaps_encode(capi.hptr(dj), P, D, capi.hptr(blobs)), "svx_dense_tmaps_encode")
+            for i, r in enumerate(top):
+                stage[o["tmaps"][r]:o["tmaps"][r] + 256] = blobs[i].ravel()
         self.dense_jobs = dj
         self.top_rec, self.tgt_rec = top, tgt
 
