@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--pairs", type=int, default=0, help="document pairs per GPU per step (0 = workload default)")
     ap.add_argument("--cost-mode", default="exact", choices=["exact", "fast", "tc"])
     ap.add_argument("--streams", type=int, default=4, help="pair groups run on separate CUDA streams (1 = serial chain)")
+    ap.add_argument("--unfused-prologue", action="store_true", help="A/B: the three separate prologue launchers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 3)")
@@ -264,6 +265,7 @@ def run_ours(args):
                    PARAMS["del_percentile_frac"], w, PARAMS["max_size_full_dp"], PARAMS["costs_sample_size"],
                    PARAMS["num_samps_for_norm"], dev, cost_mode=mode)
     cells = run.dp_cells()
+    run.fused_prologue = not args.unfused_prologue
 
     def barrier():
         torch.cuda.synchronize()

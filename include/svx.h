@@ -104,6 +104,32 @@ typedef struct SvxNormJob {
 SVX_API int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs_h, int njobs, int dim, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused level prologue: everything dp_utils.vecalign does to one side of one level before the
+ * costs (dp_utils.py:396-397, 416-418, 423-444), in the fewest passes over HBM:
+ *   (1) mean   [levels >= 1]  per-overlap mean row of the un-centred pair sums (np.mean axis=0 order)
+ *   (2) mbar   mean sample vector of the OTHER side, its sampled rows centred + unit-normalised on
+ *              the fly (they are still raw when this runs)
+ *   (3) finish one pass over the rows, a warp per row pair: subtract the mean row, unit-normalise in
+ *              place (make_norm1 arithmetic), norms = 1 - row.mbar, and the pair sums
+ *              row[2j] + row[2j+1] that are the next coarser level's input.
+ * Per-row arithmetic is identical to svx_normalize_rows / svx_downsample / svx_sample_norms; only
+ * the number of passes changes.  Both sides of a pair must be in the same call (step 2 of every job
+ * runs before step 3 of any job).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxLevelJob {
+    float *vecs;             /* (k, n, dim) raw rows (level 0) or un-centred pair sums; finished in place */
+    float *mean;             /* (k, dim) scratch for the mean rows, NULL at level 0 (nothing to subtract) */
+    float *next;             /* (k, n/2, dim) pair sums for the next coarser level, or NULL               */
+    const float *other;      /* (ko, no, dim) the other side, same level, same (unfinished) state         */
+    const float *other_mean; /* (ko, dim) the other side's `mean` (written by step 1 of its job) or NULL  */
+    const int32_t *idx;      /* (ko, per) sampled rows of `other`; NULL: leave `norms` untouched          */
+    double *mbar;            /* (dim) scratch                                                             */
+    float *norms;            /* (k, n) output, or NULL                                                    */
+    int32_t k, n, ko, no, per;
+} SvxLevelJob;
+SVX_API int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *jobs_h, int njobs, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Sampled pair scores + deletion penalty: replaces dp_core.score_path (dp_core.pyx:143-161) and
  * dp_utils.DeletionKnob / make_del_knob (dp_utils.py:43-79, 278-323).
  * scores[i] = 2(1 - e[xi].f[yi]) / (ne[xi] + nf[yi])  (fp32 denominator, no 1e-6).
@@ -225,7 +251,7 @@ SVX_API int svx_host_dense_dp(const SvxDenseJob *job_host_pointers);
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);
 SVX_API long long svx_launch_count(int reset); /* kernels launched since the last reset */
-SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec */
+SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec,7 Level */
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ extern "C" int svx_sizeof_job(int which)
         case 4: return (int)sizeof(SvxDenseJob);
         case 5: return (int)sizeof(SvxBandJob);
         case 6: return (int)sizeof(SvxAlignRec);
+        case 7: return (int)sizeof(SvxLevelJob);
         default: return -1;
     }
 }

@@ -351,6 +351,157 @@ __global__ void __launch_bounds__(256) k_del_knob(const SvxScoreJob *jobs, doubl
     if (threadIdx.x == 0) *job.del_penalty = svx_knob_finish(hist, mx, frac);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused level prologue (svx_level_prologue): the same per-row arithmetic as k_normalize /
+// k_pairsum_colmean / k_center_normalize / k_sample_mean / k_norms_gemv, in fewer passes over HBM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxLevelSamples = 2048;     // sampled rows per job whose denominators fit in smem
+
+// step 1: mean row per overlap of the un-centred pair sums (sequential fp32 accumulation over rows
+// = np.mean(axis=0)), one thread per column, 8 loads in flight.
+__global__ void __launch_bounds__(128) k_level_colmean(const SvxLevelJob *jobs, int dim)
+{
+    const SvxLevelJob job = jobs[blockIdx.y];
+    if (!job.mean || job.n <= 0) return;
+    const int cblocks = dim >> 7;
+    const int o = blockIdx.x / cblocks;
+    if (o >= job.k) return;
+    const int c = (blockIdx.x % cblocks) * 128 + threadIdx.x;
+    const float *src = job.vecs + (size_t)o * job.n * dim + c;
+    float acc = 0.0f;
+    int j = 0;
+    for (; j + 8 <= job.n; j += 8) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = __ldg(src + (size_t)(j + u) * dim);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = (j + u == 0) ? a[u] : __fadd_rn(acc, a[u]);
+    }
+    for (; j < job.n; ++j) {
+        const float a = __ldg(src + (size_t)j * dim);
+        acc = (j == 0) ? a : __fadd_rn(acc, a);
+    }
+    job.mean[(size_t)o * dim + c] = __fdiv_rn(acc, (float)job.n);
+}
+
+// step 2: mbar = mean over the sampled rows of the other side, each centred and unit-normalised on
+// the fly exactly as step 3 will finish it.  One CTA per job: warps compute the rows' denominators,
+// then one thread per column accumulates in fp64 in sample order.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_level_sample_mean(const SvxLevelJob *jobs)
+{
+    constexpr int NB = DIM / 128;
+    __shared__ __align__(16) float scratch[8][NB * kRowPad];
+    __shared__ float den_s[kMaxLevelSamples];
+    const SvxLevelJob job = jobs[blockIdx.x];
+    const int nsamp = job.ko * job.per;
+    if (!job.idx || !job.norms || nsamp <= 0 || job.no <= 0 || job.n <= 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int s = warp; s < nsamp; s += 8) {
+        const int o = s / job.per;
+        const float *p = job.other + ((size_t)o * job.no + job.idx[s]) * DIM;
+        float4 v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            v[b] = ldg_f4(p + b * 128 + 4 * lane);
+            if (job.other_mean) {
+                const float4 g = ldg_f4(job.other_mean + (size_t)o * DIM + b * 128 + 4 * lane);
+                v[b].x = __fsub_rn(v[b].x, g.x); v[b].y = __fsub_rn(v[b].y, g.y);
+                v[b].z = __fsub_rn(v[b].z, g.z); v[b].w = __fsub_rn(v[b].w, g.w);
+            }
+            float4 q;
+            q.x = __fmul_rn(v[b].x, v[b].x); q.y = __fmul_rn(v[b].y, v[b].y);
+            q.z = __fmul_rn(v[b].z, v[b].z); q.w = __fmul_rn(v[b].w, v[b].w);
+            *reinterpret_cast<float4 *>(scratch[warp] + b * kRowPad + 4 * lane) = q;
+        }
+        __syncwarp();
+        const float total = np_pairwise_from_smem<DIM>(scratch[warp], lane);
+        __syncwarp();
+        if (lane == 0) den_s[s] = __fadd_rn(__fsqrt_rn(total), 1e-5f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < DIM; c += blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < nsamp; ++s) {
+            const int o = s / job.per;
+            float x = __ldg(job.other + ((size_t)o * job.no + job.idx[s]) * DIM + c);
+            if (job.other_mean) x = __fsub_rn(x, __ldg(job.other_mean + (size_t)o * DIM + c));
+            acc += (double)__fdiv_rn(x, den_s[s]);
+        }
+        job.mbar[c] = acc / (double)nsamp;
+    }
+}
+
+// step 3: a warp per row pair (2j, 2j+1) of one overlap.
+template <int DIM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_level_finish(const SvxLevelJob *jobs)
+{
+    constexpr int NB = DIM / 128;
+    __shared__ __align__(16) float scratch[kWarpsPerCta][NB * kRowPad];
+    __shared__ double mb[DIM];
+    const SvxLevelJob job = jobs[blockIdx.y];
+    const int npair = (job.n + 1) >> 1;
+    const int64_t total = (int64_t)job.k * npair;
+    if ((int64_t)blockIdx.x * kWarpsPerCta >= total) return;
+    const bool want_norms = job.norms && job.idx && job.ko * job.per > 0 && job.no > 0;
+    if (want_norms) {
+        for (int i = threadIdx.x; i < DIM; i += blockDim.x) mb[i] = job.mbar[i];
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int half = job.n >> 1;
+    for (int64_t p = (int64_t)blockIdx.x * kWarpsPerCta + warp; p < total; p += (int64_t)gridDim.x * kWarpsPerCta) {
+        const int o = (int)(p / npair), j = (int)(p % npair);
+        float4 v[2][NB];
+        const int nrow = (2 * j + 1 < job.n) ? 2 : 1;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r >= nrow) break;
+            float *q = job.vecs + ((size_t)o * job.n + 2 * j + r) * DIM;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) v[r][b] = *reinterpret_cast<const float4 *>(q + b * 128 + 4 * lane);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (r >= nrow) break;
+            float *q = job.vecs + ((size_t)o * job.n + 2 * j + r) * DIM;
+            if (job.mean) {                 // the (k, dim) mean rows stay in L1
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const float4 g = ldg_f4(job.mean + (size_t)o * DIM + b * 128 + 4 * lane);
+                    v[r][b].x = __fsub_rn(v[r][b].x, g.x); v[r][b].y = __fsub_rn(v[r][b].y, g.y);
+                    v[r][b].z = __fsub_rn(v[r][b].z, g.z); v[r][b].w = __fsub_rn(v[r][b].w, g.w);
+                }
+            }
+            warp_unit_row<DIM>(v[r], scratch[warp], lane);
+#pragma unroll
+            for (int b = 0; b < NB; ++b) *reinterpret_cast<float4 *>(q + b * 128 + 4 * lane) = v[r][b];
+            if (want_norms) {
+                double acc = 0.0;
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const double *m = mb + b * 128 + 4 * lane;
+                    acc = fma((double)v[r][b].x, m[0], acc); acc = fma((double)v[r][b].y, m[1], acc);
+                    acc = fma((double)v[r][b].z, m[2], acc); acc = fma((double)v[r][b].w, m[3], acc);
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) job.norms[(size_t)o * job.n + 2 * j + r] = __fsub_rn(1.0f, (float)acc);
+            }
+        }
+        if (job.next && j < half) {
+            float *h = job.next + ((size_t)o * half + j) * DIM;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                float4 s4;
+                s4.x = __fadd_rn(v[0][b].x, v[1][b].x); s4.y = __fadd_rn(v[0][b].y, v[1][b].y);
+                s4.z = __fadd_rn(v[0][b].z, v[1][b].z); s4.w = __fadd_rn(v[0][b].w, v[1][b].w);
+                *reinterpret_cast<float4 *>(h + b * 128 + 4 * lane) = s4;
+            }
+        }
+    }
+}
+
 inline int rows_grid(int64_t max_rows)
 {
     int64_t g = (max_rows + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -499,5 +650,46 @@ extern "C" int svx_host_del_knob(const float *scores, int n, double frac, double
         }
     }
     *del_penalty = svx_knob_finish(hist, mx, frac);
+    return SVX_OK;
+}
+
+extern "C" int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *jobs_h, int njobs, int dim, void *stream)
+{
+    SVX_REQUIRE(svx_dim_supported(dim), SVX_ERR_UNSUPPORTED, "svx_level_prologue: dim %d not in {128,256,512,1024}", dim);
+    if (njobs <= 0) return SVX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int j = 0; j < njobs; ++j)
+        SVX_REQUIRE(!jobs_h[j].idx || jobs_h[j].ko * jobs_h[j].per <= kMaxLevelSamples, SVX_ERR_UNSUPPORTED,
+                    "svx_level_prologue: job %d draws %d samples (max %d)", j, jobs_h[j].ko * jobs_h[j].per, kMaxLevelSamples);
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int kmax = 0; int64_t mp = 0; bool any_mean = false, any_samples = false;
+        for (int j = 0; j < nj; ++j) {
+            const SvxLevelJob &jb = jobs_h[j0 + j];
+            if (jb.k > kmax) kmax = jb.k;
+            const int64_t pairs = (int64_t)jb.k * ((jb.n + 1) / 2);
+            if (pairs > mp) mp = pairs;
+            any_mean |= jb.mean != nullptr && jb.n > 0;
+            any_samples |= jb.idx != nullptr && jb.norms != nullptr && jb.ko * jb.per > 0 && jb.no > 0 && jb.n > 0;
+        }
+        if (any_mean && kmax > 0) {
+            dim3 g(kmax * (dim / 128), nj);
+            k_level_colmean<<<g, 128, 0, st>>>(jobs_d + j0, dim);
+            SVX_LAUNCH_CHECK();
+        }
+        if (any_samples) {
+#define CALL(D) k_level_sample_mean<D><<<nj, 256, 0, st>>>(jobs_d + j0)
+            SVX_DISPATCH_DIM(dim, CALL)
+#undef CALL
+            SVX_LAUNCH_CHECK();
+        }
+        if (mp > 0) {
+            dim3 g(rows_grid(mp), nj);
+#define CALL(D) k_level_finish<D><<<g, kWarpsPerCta * 32, 0, st>>>(jobs_d + j0)
+            SVX_DISPATCH_DIM(dim, CALL)
+#undef CALL
+            SVX_LAUNCH_CHECK();
+        }
+    }
     return SVX_OK;
 }

@@ -199,6 +199,7 @@ class BatchRun:
         o["tmaps"] = ar.take(np.where(is_top & (cost_mode == capi.SVX_COST_TC), 256, 0))
         # every job descriptor of the batch (upper bound incl. 16-byte alignment slack per array)
         jobs_bytes = (2 * P * capi.ROWS.itemsize + 2 * R * capi.DOWN.itemsize + 2 * R * capi.NORM.itemsize +
+                      2 * R * capi.LEVEL.itemsize + 64 * 16 +
                       R * capi.SCORE.itemsize + P * capi.DENSE.itemsize + R * capi.BAND.itemsize + 4096)
         o["jobs"] = ar.take(np.array([jobs_bytes]))
         self._jobs_off = int(o["jobs"][0])
@@ -290,6 +291,28 @@ class BatchRun:
         a_["k"], a_["n"], a_["ko"], a_["no"], a_["per"] = self.k0, rs0[sel0], self.k1, rs1[sel0], per1
         b_["vecs"], b_["other"], b_["idx"], b_["mbar"], b_["norms"] = vec1[sel1], vec0[sel1], ptr("idx1")[sel1], ptr("mbar1")[sel1], ptr("norms1")[sel1]
         b_["k"], b_["n"], b_["ko"], b_["no"], b_["per"] = self.k1, rs1[sel1], self.k0, rs0[sel1], per0
+        # fused prologue: one job per (record, side), grouped by level
+        want0 = np.zeros(R, dtype=bool); want0[sel0] = True      # norms0 computed from samples
+        want1 = np.zeros(R, dtype=bool); want1[sel1] = True
+        nxt = np.minimum(np.arange(R) + 1, max(R - 1, 0))
+        has_next = rl < self.depth[rp]
+        self.level_jobs = []
+        for lvl in range(0, lmax + 1):
+            sel = np.nonzero(rl == lvl)[0]
+            lj = np.zeros(2 * sel.size, dtype=capi.LEVEL)
+            for side, (vec_a, vec_b, mean_a, mean_b, idx_k, mbar_k, norms_k, want, ka, kb, sa, sb, per) in enumerate([
+                    (vec0, vec1, "mean0", "mean1", "idx0", "mbar0", "norms0", want0, self.k0, self.k1, rs0, rs1, per1),
+                    (vec1, vec0, "mean1", "mean0", "idx1", "mbar1", "norms1", want1, self.k1, self.k0, rs1, rs0, per0)]):
+                v = lj[side::2]
+                v["vecs"], v["other"] = vec_a[sel], vec_b[sel]
+                if lvl > 0:
+                    v["mean"], v["other_mean"] = ptr(mean_a)[sel], ptr(mean_b)[sel]
+                v["next"] = np.where(has_next[sel], vec_a[nxt[sel]], 0)
+                v["idx"] = np.where(want[sel], ptr(idx_k)[sel], 0)
+                v["norms"] = np.where(want[sel], ptr(norms_k)[sel], 0)
+                v["mbar"] = ptr(mbar_k)[sel]
+                v["k"], v["n"], v["ko"], v["no"], v["per"] = ka, sa[sel], kb, sb[sel], per
+            self.level_jobs.append((lj, np.repeat(rp[sel], 2)))
         nj_pair = np.concatenate([rp[sel0], rp[sel1]])
         order = np.argsort(nj_pair, kind="stable")       # pair-major so that a pair range is a job range
         self.norm_jobs = nj[order]
@@ -382,6 +405,8 @@ class BatchRun:
         for i, (dj_, pr_) in enumerate(self.down_jobs):
             pack(("down", i), dj_, pr_)
         pack("norm", self.norm_jobs, nj_pair)
+        for i, (lj_, pr_) in enumerate(self.level_jobs):
+            pack(("level", i), lj_, pr_)
         pack("score", self.score_jobs, rp[ssel])
         pack("dense", self.dense_jobs, np.arange(P))
         for s, groups in enumerate(self.band_stages):
@@ -436,6 +461,7 @@ class BatchRun:
         return out
 
     _events = None
+    fused_prologue = True        # False: the three separate prologue launchers (A/B measurements)
     _pair_range = None
     _streams = None
 
@@ -443,10 +469,14 @@ class BatchRun:
         """The whole path for the pairs in self._pair_range (all pairs if None) on the current stream."""
         L = capi.lib()
         D, mode = self.dim, self.cost_mode
-        self._call(L.svx_normalize_rows, "svx_normalize_rows", "rows", D)
-        for i in range(len(self.down_jobs)):
-            self._call(L.svx_downsample, "svx_downsample", ("down", i), D)
-        self._call(L.svx_sample_norms, "svx_sample_norms", "norm", D)
+        if self.fused_prologue:
+            for i in range(len(self.level_jobs)):
+                self._call(L.svx_level_prologue, "svx_level_prologue", ("level", i), D)
+        else:
+            self._call(L.svx_normalize_rows, "svx_normalize_rows", "rows", D)
+            for i in range(len(self.down_jobs)):
+                self._call(L.svx_downsample, "svx_downsample", ("down", i), D)
+            self._call(L.svx_sample_norms, "svx_sample_norms", "norm", D)
         self._call(L.svx_dense_costs, "svx_dense_costs", "dense", D, mode)
         self._call(L.svx_score_pairs, "svx_score_pairs", "score", D, mode)
         self._call(L.svx_del_knob, "svx_del_knob", "score", self.frac)
@@ -505,7 +535,14 @@ class BatchRun:
         top = self.rec_level == self.depth[self.rec_pair]
         band_l0, band_co = self.banded & l0, self.banded & ~l0
         nj = self.norm_jobs
+        lvl_bytes = 0
+        for lj, _ in self.level_jobs:
+            kk, nn = lj["k"].astype(np.int64), lj["n"].astype(np.int64)
+            rows = kk * nn * D * 4
+            lvl_bytes += int((rows * (2 + (lj["mean"] != 0)) + (lj["next"] != 0) * kk * (nn // 2) * D * 4 + kk * nn * 4 +
+                              (lj["idx"] != 0) * lj["ko"].astype(np.int64) * lj["per"] * D * 4 * 2).sum())
         out = {
+            "svx_level_prologue": lvl_bytes,
             "svx_normalize_rows": 2 * 4 * D * int(K0 * s0[l0].sum() + K1 * s1[l0].sum()),
             "svx_downsample": 4 * D * int((K0 * (s0[~top] + 3 * (s0[~top] // 2)) + K1 * (s1[~top] + 3 * (s1[~top] // 2))).sum()),
             "svx_sample_norms": int((nj["k"].astype(np.int64) * nj["n"] * (D * 4 + 4) +
