@@ -29,7 +29,7 @@ constexpr int kBC = 32;         // floats of the embedding dimension per staged 
 constexpr int kBS = kBC + 4;    // padded row stride (36 floats = 9 x 16 B: conflict-free LDS.128)
 
 template <int CX, int CY, bool TRI, bool EXACT>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, (CX <= 5 ? 2 : 1))
 k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
 {
     extern __shared__ __align__(16) float tile[];  // two slice buffers of nrows_max * kBS floats
@@ -80,26 +80,44 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
                 for (int j = 0; j < CY; ++j) acc[i][j] = 0.0f;
 
             const int xrows = CX * NX, nrows = xrows + CY * NY;
-            // slice `sl` of every touched row -> buffer sl & 1, 16 bytes per cp.async, zero-filled for
-            // rows outside the documents / overlaps (src-size 0)
-            auto issue = [&](int sl) {
-                float *buf = tile + (sl & 1) * buf_floats;
-                const int d0 = sl * kBC;
-                for (int f = tid; f < nrows * (kBC / 4); f += blockDim.x) {
+            // Every slice moves the same (row, 16-byte piece) items per thread: resolve their source rows
+            // once (the divisions by NX / NY are not cheap) and keep the pointers in registers.
+            constexpr int kMaxItems = 8;          // nrows * 8 pieces / blockDim <= 8 (checked by the launcher)
+            unsigned srco[kMaxItems];             // float offset from job.v0 / job.v1
+            unsigned from_y = 0, valid = 0;       // bit it: item reads side 1 / item has a source row
+            const int nitems = nrows * (kBC / 4);
+#pragma unroll
+            for (int it = 0; it < kMaxItems; ++it) {
+                const int f = tid + it * (int)blockDim.x;
+                srco[it] = 0;
+                if (f < nitems) {
                     const int row = f / (kBC / 4), c4 = f % (kBC / 4);
-                    const float *src = nullptr;
                     if (row < xrows) {
                         const int k = kx0 + row / NX, seg = xlo + row % NX;
-                        if (k < job.k0 && seg >= 0 && seg < s0) src = job.v0 + ((size_t)k * s0 + seg) * dim;
+                        if (k < job.k0 && seg >= 0 && seg < s0) { srco[it] = (unsigned)(((size_t)k * s0 + seg) * dim + 4 * c4); valid |= 1u << it; }
                     } else {
                         const int r2 = row - xrows;
                         const int k = ky0 + r2 / NY, seg = ylo + r2 % NY;
-                        if (k < job.k1 && seg >= 0 && seg < s1) src = job.v1 + ((size_t)k * s1 + seg) * dim;
+                        if (k < job.k1 && seg >= 0 && seg < s1) { srco[it] = (unsigned)(((size_t)k * s1 + seg) * dim + 4 * c4); valid |= 1u << it; }
+                        from_y |= 1u << it;
                     }
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + (size_t)row * kBS + 4 * c4);
-                    const float *gp = src ? src + d0 + 4 * c4 : job.v0;
-                    const int nbytes = src ? 16 : 0;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(nbytes));
+                }
+            }
+            const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
+            const float *gv0 = job.v0, *gv1 = job.v1;
+            // slice `sl` -> buffer sl & 1, 16 bytes per cp.async, zero-filled (src-size 0) for rows outside
+            // the documents / overlaps
+            auto issue = [&](int sl) {
+                const unsigned buf = tile_u32 + (unsigned)((sl & 1) * buf_floats * (int)sizeof(float));
+#pragma unroll
+                for (int it = 0; it < kMaxItems; ++it) {
+                    const int f = tid + it * (int)blockDim.x;
+                    if (f < nitems) {
+                        const float *gp = ((from_y >> it) & 1 ? gv1 : gv0) + srco[it] + sl * kBC;
+                        const int nbytes = (valid >> it) & 1 ? 16 : 0;
+                        const unsigned dst = buf + (unsigned)(((f >> 3) * kBS + 4 * (f & 7)) * (int)sizeof(float));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(nbytes));
+                    }
                 }
                 asm volatile("cp.async.commit_group;\n" ::);
             };
@@ -662,6 +680,7 @@ int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int d
     const int maxk = CX > CY ? CX : CY;
     const size_t smem = (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float);   // two slice buffers
     if (smem > 220 * 1024) return -1;
+    if ((size_t)maxk * (ta + 2 * band - 1) * (kBC / 4) > (size_t)8 * threads) return -1;   // kMaxItems per thread
     dim3 grid((max_alen + ta - 1) / ta, nj);
     if (mode == SVX_COST_EXACT) {
         auto kern = k_banded_costs<CX, CY, TRI, true>;

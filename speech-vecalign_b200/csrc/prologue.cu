@@ -348,7 +348,23 @@ __global__ void __launch_bounds__(256) k_del_knob(const SvxScoreJob *jobs, doubl
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *job.del_penalty = svx_knob_finish(hist, mx, frac);
+    // per-bin densities in parallel (exact per bin); only the fp64 running sum is sequential
+    __shared__ double dens[SVX_KNOB_BINS];
+    __shared__ long long tot_s;
+    if (threadIdx.x < 32) {
+        long long t = 0;
+        for (int i = threadIdx.x; i < SVX_KNOB_BINS; i += 32) t += hist[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (threadIdx.x == 0) tot_s = t;
+    }
+    __syncthreads();
+    if (mx > 0.0f) {
+        const float step = __fdiv_rn(mx, (float)SVX_KNOB_BINS);
+        for (int i = threadIdx.x; i < SVX_KNOB_BINS; i += blockDim.x) dens[i] = svx_knob_density(hist[i], i, step, mx, tot_s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *job.del_penalty = svx_knob_finish(dens, mx, frac);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -649,7 +665,14 @@ extern "C" int svx_host_del_knob(const float *scores, int n, double frac, double
             if (b >= 0) hist[b]++;
         }
     }
-    *del_penalty = svx_knob_finish(hist, mx, frac);
+    static thread_local double dens[SVX_KNOB_BINS];
+    long long total = 0;
+    for (int i = 0; i < SVX_KNOB_BINS; ++i) total += hist[i];
+    if (mx > 0.0f) {
+        const float step = mx / (float)SVX_KNOB_BINS;
+        for (int i = 0; i < SVX_KNOB_BINS; ++i) dens[i] = svx_knob_density(hist[i], i, step, mx, total);
+    }
+    *del_penalty = svx_knob_finish(dens, mx, frac);
     return SVX_OK;
 }
 

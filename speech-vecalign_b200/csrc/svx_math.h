@@ -118,9 +118,17 @@ SVX_HD int svx_knob_bin(float a, float maxv, float step)
     return idx;
 }
 
-// counts[1000] -> del_penalty.  maxv is max(samples) (fp32).  Degenerate maxv <= 0 follows the
-// reference's "res_max = res_min + 1e-4" branch, whose knob is 0 up to 27/28 and ends at 1e-4.
-SVX_HD double svx_knob_finish(const unsigned int *counts, float maxv, double frac)
+// density of bin i: hist[i] = counts[i] / width_i / total  (np.histogram(density=True), fp64)
+SVX_HD double svx_knob_density(unsigned int count, int i, float step, float maxv, long long total)
+{
+    const double db = (double)SVX_FSUB(svx_knob_edge(i + 1, step, maxv), svx_knob_edge(i, step, maxv));
+    return SVX_DDIV(SVX_DDIV((double)count, db), (double)total);
+}
+
+// density[1000] (svx_knob_density of every bin; may be computed in parallel) -> del_penalty.
+// maxv is max(samples) (fp32).  Degenerate maxv <= 0 follows the reference's
+// "res_max = res_min + 1e-4" branch, whose knob is 0 up to 27/28 and ends at 1e-4.
+SVX_HD double svx_knob_finish(const double *density, float maxv, double frac)
 {
     double ys[29], xs[29];
     const double qstep = SVX_DDIV(1.0, 28.0);
@@ -131,15 +139,11 @@ SVX_HD double svx_knob_finish(const unsigned int *counts, float maxv, double fra
         ys[28] = 1e-4;
     } else {
         const float step = SVX_FDIV(maxv, (float)SVX_KNOB_BINS);
-        long long total = 0;
-        for (int i = 0; i < SVX_KNOB_BINS; ++i) total += counts[i];
         const double dx = (double)SVX_FSUB(svx_knob_edge(1, step, maxv), svx_knob_edge(0, step, maxv));
         double cum = 0.0;
         int k = 1;
         for (int i = 0; i < SVX_KNOB_BINS && k < 28; ++i) {
-            double db = (double)SVX_FSUB(svx_knob_edge(i + 1, step, maxv), svx_knob_edge(i, step, maxv));
-            double h = SVX_DDIV(SVX_DDIV((double)counts[i], db), (double)total);
-            cum = (i == 0) ? h : SVX_DADD(cum, h);
+            cum = (i == 0) ? density[i] : SVX_DADD(cum, density[i]);      // np.cumsum: sequential fp64
             double cdf = SVX_DMUL(cum, dx);
             while (k < 28 && !(cdf < xs[k])) {   // searchsorted(left); NaN sorts last
                 ys[k] = SVX_DMUL(SVX_DDIV((double)i, 1000.0), (double)maxv);
