@@ -123,7 +123,7 @@ typedef struct SvxLevelJob {
     const float *other;      /* (ko, no, dim) the other side, same level, same (unfinished) state         */
     const float *other_mean; /* (ko, dim) the other side's `mean` (written by step 1 of its job) or NULL  */
     const int32_t *idx;      /* (ko, per) sampled rows of `other`; NULL: leave `norms` untouched          */
-    double *mbar;            /* (dim) scratch                                                             */
+    double *mbar;            /* (dim + 1024) scratch: mean sample vector, then 2048 fp32 denominators     */
     float *norms;            /* (k, n) output, or NULL                                                    */
     int32_t k, n, ko, no, per;
 } SvxLevelJob;

@@ -401,51 +401,72 @@ __global__ void __launch_bounds__(128) k_level_colmean(const SvxLevelJob *jobs, 
 }
 
 // step 2: mbar = mean over the sampled rows of the other side, each centred and unit-normalised on
-// the fly exactly as step 3 will finish it.  One CTA per job: warps compute the rows' denominators,
-// then one thread per column accumulates in fp64 in sample order.
+// the fly exactly as step 3 will finish it.  (a) a warp per sampled row computes its denominator
+// into the scratch behind mbar; (b) a thread per column accumulates in fp64 in sample order.
 template <int DIM>
-__global__ void __launch_bounds__(256) k_level_sample_mean(const SvxLevelJob *jobs)
+__global__ void __launch_bounds__(256) k_level_sample_den(const SvxLevelJob *jobs)
 {
     constexpr int NB = DIM / 128;
     __shared__ __align__(16) float scratch[8][NB * kRowPad];
-    __shared__ float den_s[kMaxLevelSamples];
-    const SvxLevelJob job = jobs[blockIdx.x];
+    const SvxLevelJob job = jobs[blockIdx.y];
     const int nsamp = job.ko * job.per;
     if (!job.idx || !job.norms || nsamp <= 0 || job.no <= 0 || job.n <= 0) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int s = warp; s < nsamp; s += 8) {
-        const int o = s / job.per;
-        const float *p = job.other + ((size_t)o * job.no + job.idx[s]) * DIM;
-        float4 v[NB];
+    const int s = blockIdx.x * 8 + warp;
+    if (s >= nsamp) return;
+    float *den = reinterpret_cast<float *>(job.mbar + DIM);
+    const int o = s / job.per;
+    const float *p = job.other + ((size_t)o * job.no + job.idx[s]) * DIM;
+    float4 v[NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            v[b] = ldg_f4(p + b * 128 + 4 * lane);
-            if (job.other_mean) {
-                const float4 g = ldg_f4(job.other_mean + (size_t)o * DIM + b * 128 + 4 * lane);
-                v[b].x = __fsub_rn(v[b].x, g.x); v[b].y = __fsub_rn(v[b].y, g.y);
-                v[b].z = __fsub_rn(v[b].z, g.z); v[b].w = __fsub_rn(v[b].w, g.w);
+    for (int b = 0; b < NB; ++b) {
+        v[b] = ldg_f4(p + b * 128 + 4 * lane);
+        if (job.other_mean) {
+            const float4 g = ldg_f4(job.other_mean + (size_t)o * DIM + b * 128 + 4 * lane);
+            v[b].x = __fsub_rn(v[b].x, g.x); v[b].y = __fsub_rn(v[b].y, g.y);
+            v[b].z = __fsub_rn(v[b].z, g.z); v[b].w = __fsub_rn(v[b].w, g.w);
+        }
+        float4 q;
+        q.x = __fmul_rn(v[b].x, v[b].x); q.y = __fmul_rn(v[b].y, v[b].y);
+        q.z = __fmul_rn(v[b].z, v[b].z); q.w = __fmul_rn(v[b].w, v[b].w);
+        *reinterpret_cast<float4 *>(scratch[warp] + b * kRowPad + 4 * lane) = q;
+    }
+    __syncwarp();
+    const float total = np_pairwise_from_smem<DIM>(scratch[warp], lane);
+    if (lane == 0) den[s] = __fadd_rn(__fsqrt_rn(total), 1e-5f);
+}
+
+__global__ void __launch_bounds__(128) k_level_sample_acc(const SvxLevelJob *jobs, int dim)
+{
+    const SvxLevelJob job = jobs[blockIdx.y];
+    const int nsamp = job.ko * job.per;
+    if (!job.idx || !job.norms || nsamp <= 0 || job.no <= 0 || job.n <= 0) return;
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    const float *den = reinterpret_cast<const float *>(job.mbar + dim);
+    double acc = 0.0;
+    for (int o = 0; o < job.ko; ++o) {
+        const float *base = job.other + (size_t)o * job.no * dim + c;
+        const float mu = job.other_mean ? __ldg(job.other_mean + (size_t)o * dim + c) : 0.0f;
+        const int32_t *ix = job.idx + (size_t)o * job.per;
+        const float *dn = den + (size_t)o * job.per;
+        int s = 0;
+        for (; s + 4 <= job.per; s += 4) {
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = __ldg(base + (size_t)__ldg(ix + s + u) * dim);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float xc = job.other_mean ? __fsub_rn(x[u], mu) : x[u];
+                acc += (double)__fdiv_rn(xc, dn[s + u]);
             }
-            float4 q;
-            q.x = __fmul_rn(v[b].x, v[b].x); q.y = __fmul_rn(v[b].y, v[b].y);
-            q.z = __fmul_rn(v[b].z, v[b].z); q.w = __fmul_rn(v[b].w, v[b].w);
-            *reinterpret_cast<float4 *>(scratch[warp] + b * kRowPad + 4 * lane) = q;
         }
-        __syncwarp();
-        const float total = np_pairwise_from_smem<DIM>(scratch[warp], lane);
-        __syncwarp();
-        if (lane == 0) den_s[s] = __fadd_rn(__fsqrt_rn(total), 1e-5f);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < DIM; c += blockDim.x) {
-        double acc = 0.0;
-        for (int s = 0; s < nsamp; ++s) {
-            const int o = s / job.per;
-            float x = __ldg(job.other + ((size_t)o * job.no + job.idx[s]) * DIM + c);
-            if (job.other_mean) x = __fsub_rn(x, __ldg(job.other_mean + (size_t)o * DIM + c));
-            acc += (double)__fdiv_rn(x, den_s[s]);
+        for (; s < job.per; ++s) {
+            float x = __ldg(base + (size_t)__ldg(ix + s) * dim);
+            if (job.other_mean) x = __fsub_rn(x, mu);
+            acc += (double)__fdiv_rn(x, dn[s]);
         }
-        job.mbar[c] = acc / (double)nsamp;
     }
+    job.mbar[c] = acc / (double)nsamp;
 }
 
 // step 3: a warp per row pair (2j, 2j+1) of one overlap.
@@ -686,14 +707,16 @@ extern "C" int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *
                     "svx_level_prologue: job %d draws %d samples (max %d)", j, jobs_h[j].ko * jobs_h[j].per, kMaxLevelSamples);
     for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
         const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
-        int kmax = 0; int64_t mp = 0; bool any_mean = false, any_samples = false;
+        int kmax = 0, max_samples = 0; int64_t mp = 0; bool any_mean = false, any_samples = false;
         for (int j = 0; j < nj; ++j) {
             const SvxLevelJob &jb = jobs_h[j0 + j];
             if (jb.k > kmax) kmax = jb.k;
             const int64_t pairs = (int64_t)jb.k * ((jb.n + 1) / 2);
             if (pairs > mp) mp = pairs;
             any_mean |= jb.mean != nullptr && jb.n > 0;
-            any_samples |= jb.idx != nullptr && jb.norms != nullptr && jb.ko * jb.per > 0 && jb.no > 0 && jb.n > 0;
+            const bool samp = jb.idx != nullptr && jb.norms != nullptr && jb.ko * jb.per > 0 && jb.no > 0 && jb.n > 0;
+            any_samples |= samp;
+            if (samp && jb.ko * jb.per > max_samples) max_samples = jb.ko * jb.per;
         }
         if (any_mean && kmax > 0) {
             dim3 g(kmax * (dim / 128), nj);
@@ -701,9 +724,13 @@ extern "C" int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *
             SVX_LAUNCH_CHECK();
         }
         if (any_samples) {
-#define CALL(D) k_level_sample_mean<D><<<nj, 256, 0, st>>>(jobs_d + j0)
+            dim3 ga((max_samples + 7) / 8, nj);
+#define CALL(D) k_level_sample_den<D><<<ga, 256, 0, st>>>(jobs_d + j0)
             SVX_DISPATCH_DIM(dim, CALL)
 #undef CALL
+            SVX_LAUNCH_CHECK();
+            dim3 gb(dim / 128, nj);
+            k_level_sample_acc<<<gb, 128, 0, st>>>(jobs_d + j0, dim);
             SVX_LAUNCH_CHECK();
         }
         if (mp > 0) {

@@ -214,8 +214,8 @@ class BatchRun:
         o["vec1"] = ar.take(np.where(is_l0, 0, self.k1 * rs1 * D * 4))
         o["mean0"] = ar.take(np.where(is_l0, 0, self.k0 * D * 4))
         o["mean1"] = ar.take(np.where(is_l0, 0, self.k1 * D * 4))
-        o["mbar0"] = ar.take(np.full(R, D * 8))
-        o["mbar1"] = ar.take(np.full(R, D * 8))
+        o["mbar0"] = ar.take(np.full(R, (D + 1024) * 8))     # + denominators of the sampled rows (SvxLevelJob.mbar)
+        o["mbar1"] = ar.take(np.full(R, (D + 1024) * 8))
         o["scores"] = ar.take(nsamp * 4)
         o["perm"] = ar.take(np.where(has_draw & ~is_top, nsamp * 4, 0))
         o["dcost"] = ar.take(np.where(is_top, rs0 * rs1 * 4, 0))
