@@ -247,6 +247,24 @@ SVX_API int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h, in
 SVX_API int svx_host_banded_dp(const SvxBandJob *job_host_pointers);
 SVX_API int svx_host_dense_dp(const SvxDenseJob *job_host_pointers);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host-side replay of the reference's RNG draws.  dp_utils.py:301-302,346 call
+ * np.random.choice(range(n), size=k) on the global legacy RandomState, which consumes the MT19937
+ * stream exactly like randint(0, n, k) (masked rejection on 32-bit outputs).  These two functions
+ * generate the same numbers in C: `stream` continues one state (np.random.get_state() key/pos, to be
+ * put back with set_state), `seeded` runs independent streams seeded like np.random.seed(seed), in
+ * parallel.  dst[c] receives count[c] int32 values of call c.
+ * ---------------------------------------------------------------------------------------------- */
+SVX_API int svx_host_randint_stream(uint32_t *key624, int32_t *pos, int ncalls, const int32_t *high,
+                                    const int64_t *count, int32_t *const *dst);
+SVX_API int svx_host_randint_seeded(int nstreams, const uint32_t *seeds, const int64_t *call_begin, const int32_t *high,
+                                    const int64_t *count, int32_t *const *dst, int nthreads);
+
+/* Copies nbytes (rounded up to 16) from PINNED host memory to the device with a kernel that reads the
+ * host buffer over PCIe (UVA), i.e. without the DMA queue that bulk cudaMemcpyAsync traffic occupies.
+ * For the few-MB descriptor block of a batch.  Both pointers 16-byte aligned. */
+SVX_API int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long long nbytes, void *stream);
+
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);

@@ -40,3 +40,114 @@ extern "C" int svx_sizeof_job(int which)
         default: return -1;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Host-side replay of the reference's RNG consumption (dp_utils.py:301-302,346 call
+// np.random.choice(range(n), size=k), which draws exactly like the legacy
+// RandomState.randint(0, n, k)): MT19937 + numpy's masked rejection on 32-bit outputs
+// (numpy/random/src/distributions/distributions.c random_bounded_uint64_fill, use_masked = true,
+// range < 2^32).  Written here so that a batch's ~10^7 draws cost milliseconds and, with per-pair
+// seeds, run on all host cores.
+// ------------------------------------------------------------------------------------------------
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Mt {
+    uint32_t key[624];
+    int pos;
+};
+
+inline void mt_seed(Mt &m, uint32_t seed)   // numpy legacy seeding with an integer: init_genrand
+{
+    m.key[0] = seed;
+    for (int i = 1; i < 624; ++i) m.key[i] = 1812433253u * (m.key[i - 1] ^ (m.key[i - 1] >> 30)) + (uint32_t)i;
+    m.pos = 624;
+}
+
+inline void mt_refill(Mt &m)
+{
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX = 0x9908b0dfu;
+    uint32_t *k = m.key;
+    int i = 0;
+    for (; i < 624 - 397; ++i) {
+        const uint32_t y = (k[i] & UPPER) | (k[i + 1] & LOWER);
+        k[i] = k[i + 397] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX);
+    }
+    for (; i < 623; ++i) {
+        const uint32_t y = (k[i] & UPPER) | (k[i + 1] & LOWER);
+        k[i] = k[i + (397 - 624)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX);
+    }
+    const uint32_t y = (k[623] & UPPER) | (k[0] & LOWER);
+    k[623] = k[396] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX);
+    m.pos = 0;
+}
+
+inline uint32_t mt_next(Mt &m)
+{
+    if (m.pos == 624) mt_refill(m);
+    uint32_t y = m.key[m.pos++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+inline void randint_fill(Mt &m, int32_t high, int64_t count, int32_t *out)
+{
+    const uint32_t rng = (uint32_t)(high - 1);          // randint(0, high): closed range [0, high-1]
+    if (rng == 0) { for (int64_t i = 0; i < count; ++i) out[i] = 0; return; }
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    for (int64_t i = 0; i < count; ++i) {
+        uint32_t v;
+        while ((v = (mt_next(m) & mask)) > rng) {}
+        out[i] = (int32_t)v;
+    }
+}
+
+}  // namespace
+
+// One stream: continue from (key[624], pos) — np.random.get_state()[1:3] — through `ncalls` calls
+// randint(0, high[c], count[c]) written to dst[c]; key/pos are updated for np.random.set_state.
+extern "C" int svx_host_randint_stream(uint32_t *key624, int32_t *pos, int ncalls, const int32_t *high,
+                                       const int64_t *count, int32_t *const *dst)
+{
+    if (!key624 || !pos || *pos < 0 || *pos > 624) { svx_set_error("svx_host_randint_stream: bad state"); return SVX_ERR_ARG; }
+    Mt m;
+    for (int i = 0; i < 624; ++i) m.key[i] = key624[i];
+    m.pos = *pos;
+    for (int c = 0; c < ncalls; ++c) {
+        if (high[c] < 1) { svx_set_error("svx_host_randint_stream: high %d < 1", high[c]); return SVX_ERR_ARG; }
+        randint_fill(m, high[c], count[c], dst[c]);
+    }
+    for (int i = 0; i < 624; ++i) key624[i] = m.key[i];
+    *pos = m.pos;
+    return SVX_OK;
+}
+
+// Independent streams: stream s is seeded like np.random.seed(seeds[s]) and serves calls
+// [call_begin[s], call_begin[s+1]).  Streams run on up to `nthreads` host threads.
+extern "C" int svx_host_randint_seeded(int nstreams, const uint32_t *seeds, const int64_t *call_begin, const int32_t *high,
+                                       const int64_t *count, int32_t *const *dst, int nthreads)
+{
+    if (nstreams <= 0) return SVX_OK;
+    for (int64_t c = call_begin[0]; c < call_begin[nstreams]; ++c)
+        if (high[c] < 1) { svx_set_error("svx_host_randint_seeded: high %d < 1", high[c]); return SVX_ERR_ARG; }
+    auto work = [&](int t, int nt) {
+        for (int s = t; s < nstreams; s += nt) {
+            Mt m;
+            mt_seed(m, seeds[s]);
+            for (int64_t c = call_begin[s]; c < call_begin[s + 1]; ++c) randint_fill(m, high[c], count[c], dst[c]);
+        }
+    };
+    int nt = nthreads < 1 ? 1 : nthreads;
+    if (nt > nstreams) nt = nstreams;
+    if (nt == 1) { work(0, 1); return SVX_OK; }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, t, nt);
+    for (auto &th : pool) th.join();
+    return SVX_OK;
+}

@@ -743,3 +743,29 @@ extern "C" int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *
     }
     return SVX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Descriptor upload without the DMA engines.  A batch's job descriptors and sample indices are a few
+// MB in pinned (UVA-mapped) host memory; issued as a cudaMemcpyAsync they queue behind the bulk
+// embedding copies of the following batches and delay this batch's first kernel by the whole
+// transfer.  A kernel that reads the pinned buffer over PCIe is ordered only by its own stream.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_upload(uint4 *dst, const uint4 *src, long long n16)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+}  // namespace
+
+extern "C" int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long long nbytes, void *stream)
+{
+    if (nbytes <= 0) return SVX_OK;
+    SVX_REQUIRE(((uintptr_t)dst_d & 15) == 0 && ((uintptr_t)src_pinned_h & 15) == 0, SVX_ERR_ARG, "svx_upload_pinned: 16-byte alignment required");
+    const long long n16 = (nbytes + 15) / 16;      // both buffers are padded to 256-byte multiples by the caller
+    int grid = (int)((n16 + 255) / 256);
+    if (grid > 148 * 4) grid = 148 * 4;
+    k_upload<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst_d), reinterpret_cast<const uint4 *>(src_pinned_h), n16);
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}

@@ -34,6 +34,18 @@ def _device():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, name):
+    """Long-lived side streams per device (copy stream, chunk streams): the caching allocator keys its
+    free blocks by stream, so fresh streams per call would cudaMalloc every batch."""
+    key = (dev.type, dev.index, name)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def _to_device(v, dev):
     """(K, N, D) fp32 on the device.  Returns (tensor, host_array_or_None)."""
     if isinstance(v, torch.Tensor):
@@ -71,36 +83,115 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
         logger.warning('width_over2 was set to %d, which does not make sense. increasing to 3.', width_over2)
         width_over2 = 3
     dev = _device()
-    dv, hosts = [], []
-    for v0, v1 in pairs:
-        t0, h0 = _to_device(v0, dev)
-        t1, h1 = _to_device(v1, dev)
-        if t0.shape[2] != t1.shape[2]:
-            raise AssertionError("embedding dimensions differ")
-        dv.append((t0, t1))
-        hosts.append((h0, h1))
-    if not dv:
+    pairs = list(pairs)
+    if not pairs:
         return []
-    k0, k1, dim = dv[0][0].shape[0], dv[0][1].shape[0], dv[0][0].shape[2]
-    for t0, t1 in dv:
-        if t0.shape[0] != k0 or t1.shape[0] != k1 or t0.shape[2] != dim:
+
+    def _meta(v):
+        if isinstance(v, torch.Tensor):
+            if v.dtype != torch.float32 or v.dim() != 3:
+                raise ValueError("Buffer dtype mismatch, expected 'float' (K, N, D) tensor")
+            return tuple(v.shape), v.is_cuda
+        a = np.asarray(v)
+        if a.dtype != np.float32 or a.ndim != 3:
+            # the reference's Cython buffers reject anything else (dp_core.pyx:168-171)
+            raise ValueError("Buffer dtype mismatch, expected 'float' with ndim=3")
+        return tuple(a.shape), False
+
+    metas = [(_meta(v0), _meta(v1)) for v0, v1 in pairs]
+    k0, k1, dim = metas[0][0][0][0], metas[0][1][0][0], metas[0][0][0][2]
+    for (sh0, _), (sh1, _) in metas:
+        if sh0[2] != sh1[2]:
+            raise AssertionError("embedding dimensions differ")
+        if sh0[0] != k0 or sh1[0] != k1 or sh0[2] != dim:
             raise ValueError("all pairs of a batch must share (K0, K1, D)")
-    if norms0 is not None and tuple(norms0.shape) != tuple(dv[0][0].shape[:2]):
+    if norms0 is not None and tuple(norms0.shape) != tuple(metas[0][0][0][:2]):
         raise Exception('norms0 wrong shape')          # dp_utils.py:429-432
-    if norms1 is not None and tuple(norms1.shape) != tuple(dv[0][1].shape[:2]):
+    if norms1 is not None and tuple(norms1.shape) != tuple(metas[0][1][0][:2]):
         raise Exception('norms1 wrong shape')
-    if (norms0 is not None or norms1 is not None) and len(dv) != 1:
+    if (norms0 is not None or norms1 is not None) and len(pairs) != 1:
         raise ValueError("norms0/norms1 are a single-pair option")
 
-    run = BatchRun([t0.data_ptr() for t0, _ in dv], [t1.data_ptr() for _, t1 in dv],
-                   [t0.shape[1] for t0, _ in dv], [t1.shape[1] for _, t1 in dv],
-                   k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
-                   costs_sample_size, num_samps_for_norm, dev, cost_mode=_MODES[cost_mode],
-                   norms0=norms0, norms1=norms1, keep_dense_csum=debug, seeds=seeds)
-    run.run(ngroups=(4 if len(dv) >= 8 else 1) if streams is None else int(streams))
+    # Host inputs of a large batch are pipelined: all host->device copies are queued on a copy stream up
+    # front (they run back to back at PCIe rate), and the pairs are planned and enqueued chunk by chunk,
+    # a chunk's kernels starting as soon as its embeddings have landed.  The np.random draws stay in
+    # input order because chunks are planned in input order.
+    P = len(pairs)
+    any_host = any(not c0 or not c1 for (_, c0), (_, c1) in metas)
+    nchunks = 1
+    if any_host and sync and not debug and P >= 16:
+        nchunks = min(8, P // 4)
+    bounds = [P * i // nchunks for i in range(nchunks + 1)]
+    cur = torch.cuda.current_stream(dev)
+    piped = nchunks > 1
+    copy_stream = _side_stream(dev, "copy") if piped else cur
+    dv, hosts, landed = [None] * P, [None] * P, [None] * nchunks
+
+    def queue_copies(c):
+        with torch.cuda.stream(copy_stream):
+            for p in range(bounds[c], bounds[c + 1]):
+                t0, h0 = _to_device(pairs[p][0], dev)
+                t1, h1 = _to_device(pairs[p][1], dev)
+                dv[p], hosts[p] = (t0, t1), (h0, h1)
+            landed[c] = torch.cuda.Event(enable_timing=True)
+            landed[c].record(copy_stream)
+
+    ngroups = (4 if P >= 8 else 1) if streams is None else int(streams)
+    runs = []
+    import os as _os, time as _time
+    _tr = _os.environ.get("SVX_TRACE")
+    _t0 = _time.perf_counter()
+    def _mark(what):
+        if _tr:
+            print(f"[trace] {1e3 * (_time.perf_counter() - _t0):8.2f} ms  {what}", flush=True)
+    _ev = []
+    if piped:
+        fork = torch.cuda.Event(enable_timing=True)
+        fork.record(cur)
+        copy_stream.wait_event(fork)
+    queue_copies(0)
+    for c in range(nchunks):
+        if c + 1 < nchunks:
+            queue_copies(c + 1)        # the DMA queue stays one chunk ahead of the planner
+        _mark(f"copies queued through chunk {min(c + 1, nchunks - 1)}")
+        lo, hi = bounds[c], bounds[c + 1]
+        # each chunk runs its whole chain on its own stream (4 in rotation): the latency-bound kernels of
+        # one chunk (wavefront DPs) overlap the other chunks' work and copies
+        st = _side_stream(dev, ("chunk", c % 4)) if piped else cur
+        if piped and c < 4:
+            st.wait_event(fork)
+        with torch.cuda.stream(st):
+            run = BatchRun([t0.data_ptr() for t0, _ in dv[lo:hi]], [t1.data_ptr() for _, t1 in dv[lo:hi]],
+                           [t0.shape[1] for t0, _ in dv[lo:hi]], [t1.shape[1] for _, t1 in dv[lo:hi]],
+                           k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
+                           costs_sample_size, num_samps_for_norm, dev, cost_mode=_MODES[cost_mode],
+                           norms0=norms0, norms1=norms1, keep_dense_csum=debug,
+                           seeds=None if seeds is None else list(seeds)[lo:hi])
+            _mark(f"chunk {c} planned")
+            if piped:
+                st.wait_event(landed[c])
+            if _tr and piped:
+                e_a = torch.cuda.Event(enable_timing=True); e_a.record(st)
+            run.run(ngroups=1 if piped else ngroups)
+            if _tr and piped:
+                e_b = torch.cuda.Event(enable_timing=True); e_b.record(st); _ev.append((c, e_a, e_b))
+            _mark(f"chunk {c} enqueued")
+        runs.append(run)
+    if piped:
+        for c in range(min(4, nchunks)):
+            cur.wait_stream(_side_stream(dev, ("chunk", c)))
+    run = runs[0]
     if not sync:
         return run
-    res = run.results()
+    res = []
+    if _tr:
+        torch.cuda.synchronize(dev)
+        _mark("device idle")
+        for c, e_a, e_b in _ev:
+            print(f"[trace] chunk {c}: copies landed {fork.elapsed_time(landed[c]):7.2f}  kernels start {fork.elapsed_time(e_a):7.2f}  end {fork.elapsed_time(e_b):7.2f} ms", flush=True)
+    for r_ in runs:
+        res.extend(r_.results())
+    _mark("results read")
     for p, r in enumerate(res):
         if r["status"]:
             # the reference fails here with IndexError / 'traceback bug' (dp_utils.py:123-124)

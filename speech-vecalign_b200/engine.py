@@ -8,6 +8,8 @@ Nothing here computes alignment arithmetic on the CPU: numpy is used for shapes,
 draws (the reference draws from the global ``np.random`` stream, dp_utils.py:301-302,346) and for
 unpacking results.
 """
+import os
+from concurrent.futures import ThreadPoolExecutor
 from math import ceil
 
 import numpy as np
@@ -83,26 +85,87 @@ def draw_samples(rec_s0, rec_s1, pair_first, pair_nlev, k0, k1, num_samps_for_no
     idx0 = np.zeros((nrec, k1, per1), dtype=np.int32)
     idx1 = np.zeros((nrec, k0, per0), dtype=np.int32)
     knob = [None] * nrec
-    for p in range(pair_first.shape[0]):
+
+    def draw_pair(p, rs):
+        """All draws of pair p from the RandomState-like `rs`, in the reference's call order."""
         first, nlev = int(pair_first[p]), int(pair_nlev[p])
-        if seeds is not None:                     # per-pair stream: independent of batch order / sharding
-            np.random.seed(int(seeds[p]))
         for r in range(first, first + nlev):
             a, b = int(rec_s0[r]), int(rec_s1[r])
             lvl0 = r == first
             if not (lvl0 and skip_norm0) and b and per1:
                 for o in range(k1):
-                    idx0[r, o] = np.random.randint(0, b, per1)
+                    idx0[r, o] = rs.randint(0, b, per1)
             if not (lvl0 and skip_norm1) and a and per0:
                 for o in range(k0):
-                    idx1[r, o] = np.random.randint(0, a, per0)
+                    idx1[r, o] = rs.randint(0, a, per0)
         for r in range(first, first + nlev):
             a, b = int(rec_s0[r]), int(rec_s1[r])
             if a > 0 and b > 0 and costs_sample_size > 0 and a * b >= costs_sample_size:
-                xi = np.random.randint(0, a, costs_sample_size).astype(np.int32)
-                yi = np.random.randint(0, b, costs_sample_size).astype(np.int32)
+                xi = rs.randint(0, a, costs_sample_size).astype(np.int32)
+                yi = rs.randint(0, b, costs_sample_size).astype(np.int32)
                 knob[r] = (xi, yi)
+
+    npairs = pair_first.shape[0]
+    if seeds is None:
+        for p in range(npairs):                          # the global stream: inherently sequential
+            draw_pair(p, np.random)
+    elif npairs < 4:
+        for p in range(npairs):
+            draw_pair(p, np.random.RandomState(int(seeds[p])))
+    else:
+        # per-pair streams are independent (RandomState(seed) == np.random after np.random.seed(seed)) and
+        # randint releases the GIL: draw the pairs on a thread pool
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda p: draw_pair(p, np.random.RandomState(int(seeds[p]))), range(npairs)))
     return idx0, idx1, knob, per0, per1
+
+
+def draw_samples_into(stage, off, rs0, rs1, rec_pair, rec_level, k0, k1, per0, per1, sample_size, has_draw,
+                      skip_norm0, skip_norm1, seeds):
+    """The reference's RNG draws of a batch, written at their final place in the (pinned) staging
+    buffer.  Call order per pair: for each level ascending the n0 draws (K1 calls
+    over range(size1), dp_utils.py:346), then the n1 draws (K0 calls over range(size0)); then for each
+    level ascending the knob draws x, y (dp_utils.py:301-302) iff size0*size1 >= sample_size.
+    seeds is None: the global np.random stream, pair after pair (what a serial loop of the reference
+    consumes).  seeds given: pair p draws from RandomState(seeds[p]); the streams are independent, so
+    they are generated by libsvx's bit-exact MT19937/randint replay on all host cores.
+    Returns knob[r] = (xi, yi) int32 views into `stage` (or None)."""
+    R = rs0.shape[0]
+    rec = np.arange(R)
+    l0 = rec_level == 0
+    c0 = ~(l0 & skip_norm0) & (rs1 > 0) & (per1 > 0)          # n0 draws of record r happen
+    c1 = ~(l0 & skip_norm1) & (rs0 > 0) & (per0 > 0)
+    parts = []      # (pair, phase, rec, sub, high, count, dst offset)
+    for cond, k, per, high, key in ((c0, k1, per1, rs1, "idx0"), (c1, k0, per0, rs0, "idx1")):
+        r = np.repeat(rec[cond], k)
+        sub = np.tile(np.arange(k), int(cond.sum())) + (0 if key == "idx0" else 1000)
+        parts.append((rec_pair[r], np.zeros_like(r), r, sub, high[r], np.full(r.shape, per, dtype=np.int64),
+                      off[key][r] + (sub % 1000) * per * 4))
+    r = rec[has_draw]
+    for sub, high, key in ((0, rs0, "xi"), (1, rs1, "yi")):
+        parts.append((rec_pair[r], np.ones_like(r), r, np.full(r.shape, sub), high[r],
+                      np.full(r.shape, sample_size, dtype=np.int64), off[key][r]))
+    pair, phase, recs, sub, high, count, dst = (np.concatenate([p[i] for p in parts]) for i in range(7))
+    order = np.lexsort((sub, recs, phase, pair))
+    pair, high, count, dst = pair[order], high[order].astype(np.int32), count[order].astype(np.int64), dst[order].astype(np.int64)
+    ncalls = pair.shape[0]
+    if ncalls:
+        if seeds is None:
+            for c in range(ncalls):
+                n = int(count[c])
+                stage[dst[c]:dst[c] + 4 * n].view(np.int32)[:] = np.random.randint(0, int(high[c]), n)
+        else:
+            npairs = int(rec_pair.max()) + 1 if R else 0
+            begin = np.searchsorted(pair, np.arange(npairs + 1)).astype(np.int64)
+            sd = np.ascontiguousarray(np.asarray(seeds, dtype=np.int64)[:npairs] & 0xFFFFFFFF, dtype=np.uint32)
+            ptrs = (stage.ctypes.data + dst).astype(np.uint64)
+            capi.check(capi.lib().svx_host_randint_seeded(npairs, capi.hptr(sd), capi.hptr(begin), capi.hptr(high), capi.hptr(count),
+                                                          capi.hptr(ptrs), min(32, os.cpu_count() or 1)), "svx_host_randint_seeded")
+    knob = [None] * R
+    for r in np.nonzero(has_draw)[0]:
+        n = 4 * sample_size
+        knob[r] = (stage[off["xi"][r]:off["xi"][r] + n].view(np.int32), stage[off["yi"][r]:off["yi"][r] + n].view(np.int32))
+    return knob
 
 
 def fallback_del_penalty(frac):
@@ -172,17 +235,15 @@ class BatchRun:
         T = np.where(is_l0, len(self.types), 1)
         self.T = T
 
-        # ---- host RNG draws (reference order) -------------------------------------------------
-        self.idx0, self.idx1, self.knob, per0, per1 = draw_samples(
-            rs0, rs1, self.first, self.nlev, self.k0, self.k1, int(num_samps_for_norm), self.sample_size,
-            norms0 is not None, norms1 is not None, seeds=seeds)
+        # ---- sampling plan (sizes only; the draws themselves go straight into the staging buffer) ------
+        per1 = ceil(int(num_samps_for_norm) / self.k1) if self.k1 else 0   # samples per overlap of side 1 (for n0)
+        per0 = ceil(int(num_samps_for_norm) / self.k0) if self.k0 else 0
         self.per0, self.per1 = per0, per1
-        nsamp = np.zeros(R, dtype=np.int64)
-        for r in range(R):
-            a, b = int(rs0[r]), int(rs1[r])
-            if a > 0 and b > 0 and self.sample_size > 0:
-                nsamp[r] = a * b if a * b < self.sample_size else self.sample_size
+        prod = rs0 * rs1
+        nsamp = np.where((rs0 > 0) & (rs1 > 0) & (self.sample_size > 0), np.minimum(prod, self.sample_size), 0).astype(np.int64)
         self.nsamp = nsamp
+        # dp_utils.py:288-302: the full grid when e*f < sample_size, two RNG draws otherwise
+        has_draw = (rs0 > 0) & (rs1 > 0) & (self.sample_size > 0) & (prod >= self.sample_size)
 
         # ---- arena layout ---------------------------------------------------------------------
         ar = _Arena()
@@ -191,7 +252,6 @@ class BatchRun:
         # host-initialised region first (one H2D copy)
         o["idx0"] = ar.take(np.full(R, self.k1 * per1 * 4))
         o["idx1"] = ar.take(np.full(R, self.k0 * per0 * 4))
-        has_draw = np.array([k is not None for k in self.knob])
         o["xi"] = ar.take(np.where(has_draw, nsamp * 4, 0))
         o["yi"] = ar.take(np.where(has_draw, nsamp * 4, 0))
         o["delpen"] = ar.take(np.full(R, 8))
@@ -244,18 +304,17 @@ class BatchRun:
         self.arena[st_lo:self.nbytes].zero_()
 
         # ---- host staging of the host-initialised region ---------------------------------------
-        stage = np.zeros(host_end, dtype=np.uint8)
+        # pinned staging (torch's caching host allocator recycles it): the single H2D copy below is then
+        # asynchronous, so planning the next batch never waits for this batch's kernels
+        self._stage = torch.zeros(host_end, dtype=torch.uint8, pin_memory=True)
+        stage = self._stage.numpy()
         fb = fallback_del_penalty(self.frac)
-        for r in range(R):
-            if self.k1 * per1:
-                stage[o["idx0"][r]:o["idx0"][r] + self.k1 * per1 * 4] = self.idx0[r].view(np.uint8).ravel()
-            if self.k0 * per0:
-                stage[o["idx1"][r]:o["idx1"][r] + self.k0 * per0 * 4] = self.idx1[r].view(np.uint8).ravel()
-            if self.knob[r] is not None:
-                xi, yi = self.knob[r]
-                stage[o["xi"][r]:o["xi"][r] + xi.nbytes] = xi.view(np.uint8)
-                stage[o["yi"][r]:o["yi"][r] + yi.nbytes] = yi.view(np.uint8)
-            stage[o["delpen"][r]:o["delpen"][r] + 8] = np.array([fb], dtype=np.float64).view(np.uint8)
+        if R:
+            dp_view = np.full(R, fb, dtype=np.float64)
+            for r in range(R):
+                stage[o["delpen"][r]:o["delpen"][r] + 8] = dp_view[r:r + 1].view(np.uint8)
+        self.knob = draw_samples_into(stage, o, rs0, rs1, rp, rl, self.k0, self.k1, per0, per1, self.sample_size,
+                                      has_draw, norms0 is not None, norms1 is not None, seeds)
 
         # ---- job descriptors ------------------------------------------------------------------
         b = self.base
@@ -412,8 +471,11 @@ class BatchRun:
         for s, groups in enumerate(self.band_stages):
             for g, (bj, pr_) in enumerate(groups):
                 pack(("band", s, g), bj, pr_)
-        self._stage = torch.from_numpy(stage)
-        self.arena[:host_end].copy_(self._stage, non_blocking=False)
+        # descriptor block -> device by a kernel reading the pinned buffer (not the DMA queue, which the bulk
+        # embedding copies of the following batches occupy)
+        if host_end:
+            capi.check(capi.lib().svx_upload_pinned(self.base, self._stage.data_ptr(), host_end,
+                                                    torch.cuda.current_stream(device).cuda_stream), "svx_upload_pinned")
         if norms0 is not None:
             self._put(o["norms0"][self.first[0]], np.ascontiguousarray(norms0, dtype=np.float32))
         if norms1 is not None:

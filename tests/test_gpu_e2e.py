@@ -179,3 +179,26 @@ def test_stream_groups_do_not_change_results(svb, oracle):
         al, sc = records_to_alignments(r["recs"])
         assert same_alignments(al, ref[0]["final_alignments"])
         assert np.max(np.abs(sc - ref[0]["alignment_scores"])) <= 1e-4
+
+
+def test_chunked_host_pipeline_equals_serial_loop(svb, oracle):
+    """>= 16 host pairs take the chunk-pipelined path of vecalign_batch (copies queued on a copy
+    stream, chunks planned in input order): the global np.random stream must still be consumed exactly
+    as a serial loop of the reference consumes it."""
+    from speech_vecalign_b200 import synth
+    rng = np.random.default_rng(3)
+    shapes = [(int(a), int(b)) for a, b in zip(rng.integers(40, 420, 19), rng.integers(40, 420, 19))]
+    a, k = 4, 3
+    types = oracle.alignment_types(a)
+    args = (types, 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    pairs = [synth.synth_pair(n0, n1, k, dim=256, seed=900 + i) for i, (n0, n1) in enumerate(shapes)]
+    np.random.seed(11)
+    refs = [oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True) for v0, v1 in pairs]
+    ref_state = np.random.get_state()[1].copy()
+    np.random.seed(11)
+    gots = svb.vecalign_batch([(v0.copy(), v1.copy()) for v0, v1 in pairs], *args)
+    assert np.array_equal(ref_state, np.random.get_state()[1])
+    assert len(gots) == len(refs)
+    for r, g in zip(refs, gots):
+        assert same_alignments(g[0]["final_alignments"], r[0]["final_alignments"])
+        assert np.max(np.abs(g[0]["alignment_scores"] - r[0]["alignment_scores"]), initial=0) <= 1e-4

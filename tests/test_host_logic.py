@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(svb):
 def test_struct_layouts_match(svb):
     L = svb.capi.lib()
     for i, dt in enumerate([svb.capi.ROWS, svb.capi.DOWN, svb.capi.NORM, svb.capi.SCORE, svb.capi.DENSE,
-                            svb.capi.BAND, svb.capi.REC]):
+                            svb.capi.BAND, svb.capi.REC, svb.capi.LEVEL]):
         assert L.svx_sizeof_job(i) == dt.itemsize
 
 
@@ -238,3 +238,60 @@ def test_planner_replays_reference_rng_stream(svb, oracle, n0, n1, a):
     np.random.seed(77)
     engine.draw_samples(S0[0, :nlev[0]], S1[0, :nlev[0]], np.array([0]), nlev, k, k, 100, 20000, False, False)
     assert np.array_equal(np.random.get_state()[1], want)
+
+
+@pytest.mark.parametrize("seeded", [False, True])
+def test_draws_into_staging_match_reference_order(svb, seeded):
+    """draw_samples_into (vectorised call list; C MT19937 replay for per-pair seeds) must produce
+    exactly the numbers of the straightforward draw_samples loop, which is itself pinned to the
+    reference's stream above — including the global stream's final state."""
+    from speech_vecalign_b200 import engine
+    n0 = [237, 700, 90, 0, 3, 2000, 1]
+    n1 = [217, 650, 80, 5, 2000, 2000, 1]
+    k0, k1, nsfn, ss = 3, 4, 100, 20000
+    depth, S0, S1 = engine.level_sizes(n0, n1, 300)
+    nlev = depth + 1
+    first = np.concatenate([[0], np.cumsum(nlev)[:-1]])
+    rp = np.repeat(np.arange(len(n0)), nlev)
+    rl = np.arange(int(nlev.sum())) - first[rp]
+    rs0, rs1 = S0[rp, rl], S1[rp, rl]
+    seeds = [11 + 3 * i for i in range(len(n0))] if seeded else None
+    np.random.seed(5)
+    idx0, idx1, knob, per0, per1 = engine.draw_samples(rs0, rs1, first, nlev, k0, k1, nsfn, ss, False, False, seeds=seeds)
+    state_ref = np.random.get_state()[1].copy()
+    R = rs0.shape[0]
+    has_draw = (rs0 > 0) & (rs1 > 0) & (rs0 * rs1 >= ss)
+    assert [k is not None for k in knob] == list(has_draw)
+    ar = engine._Arena()
+    off = {"idx0": ar.take(np.full(R, k1 * per1 * 4)), "idx1": ar.take(np.full(R, k0 * per0 * 4)),
+           "xi": ar.take(np.where(has_draw, ss * 4, 0)), "yi": ar.take(np.where(has_draw, ss * 4, 0))}
+    stage = np.zeros(ar.top, dtype=np.uint8)
+    np.random.seed(5)
+    knob2 = engine.draw_samples_into(stage, off, rs0, rs1, rp, rl, k0, k1, per0, per1, ss, has_draw, False, False, seeds)
+    if not seeded:
+        assert np.array_equal(np.random.get_state()[1], state_ref)
+    for r in range(R):
+        got0 = stage[off["idx0"][r]:off["idx0"][r] + k1 * per1 * 4].view(np.int32).reshape(k1, per1)
+        got1 = stage[off["idx1"][r]:off["idx1"][r] + k0 * per0 * 4].view(np.int32).reshape(k0, per0)
+        assert np.array_equal(got0, idx0[r]) and np.array_equal(got1, idx1[r]), r
+        if knob[r] is not None:
+            assert np.array_equal(knob2[r][0], knob[r][0]) and np.array_equal(knob2[r][1], knob[r][1]), r
+        else:
+            assert knob2[r] is None
+
+
+def test_c_randint_replay_equals_numpy(svb):
+    L = svb.capi.lib()
+    np.random.seed(99)
+    np.random.randint(0, 5, 333)
+    st = np.random.get_state()
+    key, pos = st[1].copy(), np.array([st[2]], dtype=np.int32)
+    highs = np.array([1, 2, 3, 255, 256, 257, 20000, 2 ** 31 - 1], dtype=np.int32)
+    counts = np.array([4, 9, 100, 1000, 1000, 1000, 5000, 50], dtype=np.int64)
+    outs = [np.zeros(int(c), np.int32) for c in counts]
+    ptrs = np.array([o.ctypes.data for o in outs], dtype=np.uint64)
+    assert L.svx_host_randint_stream(key.ctypes.data, pos.ctypes.data, len(outs), highs.ctypes.data, counts.ctypes.data, ptrs.ctypes.data) == 0
+    for h, c, o in zip(highs, counts, outs):
+        assert np.array_equal(np.random.randint(0, int(h), int(c)), o)
+    st2 = np.random.get_state()
+    assert np.array_equal(st2[1], key) and st2[2] == pos[0]
