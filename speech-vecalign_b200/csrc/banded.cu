@@ -460,13 +460,32 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 #pragma unroll
     for (int s = 0; s <= NH; ++s) { hist[s] = INFINITY; bofh[s] = 0; }
 
-    // best alignment-type candidate of diagonal `aa` (band offset bo_a, staged costs crow) given that
-    // hist[k]/bofh[k] describe diagonal aa - HOFF - k ... i.e. the caller is HOFF diagonals behind.
-    // Two independent strict-'<' chains (first half / second half of the type list) halve the
-    // dependent compare-select latency and keep the reference's first-minimum tie-break.
-    auto type_candidates = [&](auto hoff_tag, int bo_a, const float *crow, double &best_out, int &code_out) {
+    // Everything about diagonal a_t that does not depend on the diagonal right before it: band
+    // geometry, the boundary / out-of-lattice override, and the best alignment-type candidate (types
+    // reach back >= 2 diagonals).  HOFF = 1 when called one diagonal ahead (history registers still
+    // describe a_t - 1 as "current").  Two independent strict-'<' chains (first / second half of the
+    // type list) halve the dependent compare-select latency and keep the first-minimum tie-break.
+    struct Prep {
+        double tbest, ovr_val;     // best type candidate; value forced when `ovr`
+        int tcode, ovr_code, d1, bo;
+        bool ovr;
+    };
+    auto prepare = [&](auto hoff_tag, int a_t, int bo_t, int bo_prev, const float *crow) {
         constexpr int HOFF = decltype(hoff_tag)::value;
         constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
+        Prep p;
+        p.bo = bo_t;
+        p.d1 = bo_t - bo_prev;
+        const int yy = lane + bo_t, xx = a_t - yy;
+        // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the deletions -
+        // reference quirk, dp_core.pyx:382,390); lanes >= B and lattice nodes outside the documents hold
+        // +inf, so predecessors outside the node band never win the strict '<' (no range tests below)
+        const bool cell_ok = lane < B && xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && a_t - 2 < A;
+        const bool by = lane < B && xx == 0 && yy >= 0 && yy <= s1;           // csum = pen * yy, bp (0,1)
+        const bool bx = lane < B && !by && yy == 0 && xx >= 0 && xx <= s0;    // csum = pen * xx, bp (1,0)
+        p.ovr = !cell_ok;
+        p.ovr_val = by ? __dmul_rn(pen, (double)yy) : (bx ? __dmul_rn(pen, (double)xx) : (double)INFINITY);
+        p.ovr_code = by ? T : (bx ? T + 1 : SVX_BP_NONE);
         double b0 = INFINITY, b1 = INFINITY;
         int c0 = SVX_BP_NONE, c1 = SVX_BP_NONE;
         int t = 0;
@@ -475,15 +494,16 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 #pragma unroll
             for (int y = 1; x + y <= K + 1; ++y, ++t) {
                 const int s = x + y;                       // >= 2, so s - HOFF >= 1
-                const int src = lane + (bo_a - bofh[s - HOFF]) - y;
-                const double pv = __shfl_sync(0xffffffffu, hist[s - HOFF], src & 31);
+                const int src = lane + (bo_t - bofh[s - HOFF]) - y;
+                const double pv = __shfl_sync(0xffffffffu, hist[s - HOFF], src);
                 const double tot = __dadd_rn(pv, (double)crow[t * B]);
                 if (t < SPLIT) { if (tot < b0) { b0 = tot; c0 = t; } }
                 else { if (tot < b1) { b1 = tot; c1 = t; } }
             }
         }
         if (SPLIT < T && b1 < b0) { b0 = b1; c0 = c1; }
-        best_out = b0; code_out = c0;
+        p.tbest = b0; p.tcode = c0;
+        return p;
     };
     using Tag0 = std::integral_constant<int, 0>;
     using Tag1 = std::integral_constant<int, 1>;
@@ -499,46 +519,33 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             const int *bo = (c & 1) ? bbuf1 : bbuf0;
             const int start = c * kChunk;
             const int end = min(start + kChunk, nodes_a);
-            double tbest; int tcode;
-            type_candidates(Tag0{}, bo[0], cb + lane, tbest, tcode);
+            uint8_t *bp_out = g_bp + (size_t)start * B + lane;
+            double *cs_out = g_csum + (size_t)start * B + lane;
+            Prep cur = prepare(Tag0{}, start, bo[0], bofh[1], cb + lane);
             for (int aa = start; aa < end; ++aa) {
-                const int bo0 = bo[aa - start];
-                // software pipeline: the type candidates of diagonal aa+1 only read diagonals <= aa-1,
-                // so they are issued here, beside the latency chain of diagonal aa
-                double nbest = INFINITY; int ncode = SVX_BP_NONE;
-                if (aa + 1 < end) {
-                    // relative to aa+1 the history is one diagonal behind: bofh[] lacks boff(aa)
-                    const int keep = bofh[0];
-                    bofh[0] = bo0;
-                    type_candidates(Tag1{}, bo[aa + 1 - start], cb + (size_t)(aa + 1 - start) * tb + lane, nbest, ncode);
-                    bofh[0] = keep;
-                }
-                const int yy = lane + bo0, xx = aa - yy;
-                // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the
-                // deletions - reference quirk, dp_core.pyx:382,390)
-                const bool cell_ok = lane < B && xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && aa - 2 < A;
-                double best = tbest;
-                int code = tcode;
-                {
-                    const double hp = __dadd_rn(hist[1], pen);
-                    const int d1 = bo0 - bofh[1];
-                    double tot = __shfl_sync(0xffffffffu, hp, (lane + d1 - 1) & 31);     // (0,1): consume y
-                    if (tot < best) { best = tot; code = T; }
-                    tot = __shfl_sync(0xffffffffu, hp, (lane + d1) & 31);                // (1,0): consume x
-                    if (tot < best) { best = tot; code = T + 1; }
-                }
-                if (!cell_ok) { best = INFINITY; code = SVX_BP_NONE; }
+                // software pipeline: diagonal aa+1 is prepared here, beside the latency chain of aa
+                Prep nxt = cur;
+                if (aa + 1 < end)
+                    nxt = prepare(Tag1{}, aa + 1, bo[aa + 1 - start], cur.bo, cb + (size_t)(aa + 1 - start) * tb + lane);
+                // the chain: csum(aa-1) -> + pen -> shuffle -> two compare-selects -> override -> csum(aa)
+                double best = cur.tbest;
+                int code = cur.tcode;
+                const double hp = __dadd_rn(hist[1], pen);
+                double tot = __shfl_sync(0xffffffffu, hp, lane + cur.d1 - 1);        // (0,1): consume y
+                if (tot < best) { best = tot; code = T; }
+                tot = __shfl_sync(0xffffffffu, hp, lane + cur.d1);                   // (1,0): consume x
+                if (tot < best) { best = tot; code = T + 1; }
+                if (cur.ovr) { best = cur.ovr_val; code = cur.ovr_code; }
                 if (lane < B) {
-                    if (xx == 0 && yy >= 0 && yy <= s1) { best = __dmul_rn(pen, (double)yy); code = T; }
-                    else if (yy == 0 && xx >= 0 && xx <= s0) { best = __dmul_rn(pen, (double)xx); code = T + 1; }
-                    g_bp[(size_t)aa * B + lane] = (uint8_t)code;
-                    g_csum[(size_t)aa * B + lane] = best;
+                    *bp_out = (uint8_t)code;
+                    *cs_out = best;
                 }
+                bp_out += B; cs_out += B;
 #pragma unroll
                 for (int s = NH; s >= 2; --s) { hist[s] = hist[s - 1]; bofh[s] = bofh[s - 1]; }
                 hist[1] = best;
-                bofh[1] = bo0;
-                tbest = nbest; tcode = ncode;
+                bofh[1] = cur.bo;
+                cur = nxt;
             }
         }
         __syncthreads();
