@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 
     // ---- phase 2: backpointer walk through a shared-memory window ---------------------------------
     int *wboff = reinterpret_cast<int *>(smem_raw);
-    uint8_t *wbp = reinterpret_cast<uint8_t *>(wboff + win_diags);
+    uint8_t *wbp = reinterpret_cast<uint8_t *>(wboff + ((win_diags + 8 + 3) & ~3));     // 16-byte aligned
     const int cap = job.rec_cap;
     if (tid == 0) {
         wst[0] = s0; wst[1] = s1; wst[2] = 0;
@@ -564,10 +564,15 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     __syncthreads();
     while (!wst[4]) {
         const int top = wst[0] + wst[1];
-        const int hi = top + 1, lo = max(0, hi - win_diags);
+        // window [lo, hi): lo rounded down to a multiple of 8 diagonals so that its first backpointer is
+        // 16-byte aligned (B is even) and the bulk of the window moves as uint4
+        const int hi = top + 1, lo = max(0, hi - win_diags) & ~7;
         for (int i = tid; i < hi - lo; i += blockDim.x) wboff[i] = svx_boff_out(job.ypath, lo + i, w);
         const uint8_t *bsrc = job.bp + (size_t)lo * B;
-        for (int i = tid; i < (hi - lo) * B; i += blockDim.x) wbp[i] = bsrc[i];
+        const int nbytes = (hi - lo) * B, n16 = nbytes >> 4;
+        for (int i = tid; i < n16; i += blockDim.x)
+            reinterpret_cast<uint4 *>(wbp)[i] = __ldcg(reinterpret_cast<const uint4 *>(bsrc) + i);
+        for (int i = (n16 << 4) + tid; i < nbytes; i += blockDim.x) wbp[i] = bsrc[i];
         __syncthreads();
         if (tid == 0) {
             int x = wst[0], y = wst[1], cnt = wst[2], st = SVX_ST_OK;
@@ -772,7 +777,7 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
     const int win_cap = (96 * 1024) / per_diag;
     if (win > win_cap) win = win_cap;
     if (win < 64) win = 64;
-    const size_t walk_bytes = (size_t)win * per_diag + 16;
+    const size_t walk_bytes = (size_t)(win + 12) * per_diag + 32;     // + the 8-diagonal alignment slack
     const size_t smem = dp_bytes > walk_bytes ? dp_bytes : walk_bytes;
     auto kern = k_banded_dp_tri<K>;
     if (smem > 40 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

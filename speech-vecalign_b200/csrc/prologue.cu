@@ -261,7 +261,6 @@ constexpr int kScStride = 36;
 template <bool EXACT>
 __global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob *jobs, int dim)
 {
-    __shared__ __align__(16) float sx[kScWarps][32 * kScStride];
     __shared__ __align__(16) float sy[kScWarps][32 * kScStride];
     const SvxScoreJob job = jobs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -280,31 +279,28 @@ __global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob
     if (job.dots) {
         if (valid) dot = job.dots[(size_t)xi * job.nf + yi];
     } else {
-        // rows fetched by this lane in load step g: sample 4g + lane/8, 16-byte piece lane%8
+        // y rows: fetched by this lane in load step g: sample 4g + lane/8, 16-byte piece lane%8.
+        // x rows: the samples are sorted by x, so the warp's 32 samples share a handful of x rows; each
+        // lane reads its own x row directly (lanes with the same row hit the same 16 bytes: one L1
+        // tag per distinct row), no staging.
         const int sub = lane >> 3, piece = 4 * (lane & 7);
-        int xr[8], yr[8];
+        int yr[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            xr[g] = __shfl_sync(0xffffffffu, xi, 4 * g + sub);
-            yr[g] = __shfl_sync(0xffffffffu, yi, 4 * g + sub);
-        }
-        float *mx = sx[warp], *my = sy[warp];
+        for (int g = 0; g < 8; ++g) yr[g] = __shfl_sync(0xffffffffu, yi, 4 * g + sub);
+        float *my = sy[warp];
+        const float *xrow = job.e + (size_t)xi * dim;
         for (int d0 = 0; d0 < dim; d0 += 32) {
-            float4 vx[8], vy[8];
+            float4 vy[8], vx[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                vx[g] = ldg_f4(job.e + (size_t)xr[g] * dim + d0 + piece);
-                vy[g] = ldg_f4(job.f + (size_t)yr[g] * dim + d0 + piece);
-            }
+            for (int g = 0; g < 8; ++g) vy[g] = ldg_f4(job.f + (size_t)yr[g] * dim + d0 + piece);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                *reinterpret_cast<float4 *>(mx + (4 * g + sub) * kScStride + piece) = vx[g];
-                *reinterpret_cast<float4 *>(my + (4 * g + sub) * kScStride + piece) = vy[g];
-            }
+            for (int q = 0; q < 8; ++q) vx[q] = ldg_f4(xrow + d0 + 4 * q);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) *reinterpret_cast<float4 *>(my + (4 * g + sub) * kScStride + piece) = vy[g];
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 a = *reinterpret_cast<const float4 *>(mx + lane * kScStride + 4 * q);
+                const float4 a = vx[q];
                 const float4 b = *reinterpret_cast<const float4 *>(my + lane * kScStride + 4 * q);
                 if (EXACT) {
                     dot = __fadd_rn(dot, __fmul_rn(a.x, b.x)); dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));

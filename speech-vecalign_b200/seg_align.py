@@ -1,0 +1,179 @@
+"""Batch driver for step 5.4 of the Speech-Vecalign pipeline — the GPU replacement of
+``svecalign/seg_align/align.py`` (reference: a serial loop calling ``vecalign.align`` once per document
+pair, align.py:206-230).
+
+Same command line (positional ``metadata out_dir``; ``--src_lang --tgt_lang --seg_dir --concat_dir
+--embed_dir --is_stopes_embed --fp16_embed -a --search_buffer_size -d --max_size_full_dp
+--costs_sample_size --num_samps_for_norm --ign_indices_dir``, align.py:13-96), same file conventions
+(``<dir>/<lang>/<audio stem>.txt|.embed``, ignore files ``<src>-<tgt>.{src,tgt}.txt``, output
+``out_dir/<src>-<tgt>/<src stem>-<tgt stem>.txt``, align.py:117-179) and the same output format
+(vecalign.py:174-184).  What changes is the execution: pairs are grouped into GPU batches bounded by
+``--batch_gb`` of embeddings, every batch is one ``vecalign_batch`` call (one kernel launch per stage
+for all its pairs), and with several processes (``torchrun`` or ``--rank/--n_shard``) the pairs are
+length-balanced across GPUs; no collective is needed because every process writes its own files.
+
+Additions: ``--skip_existing`` (the reference's slow stages do this, preprocess/segment.py:105-128),
+``--seed`` (the reference draws from the unseeded global RNG; here pair i draws from
+RandomState(crc32(output name) ^ seed), so results do not depend on batching or sharding),
+``--cost_mode exact|fast|tc``.
+
+    python -m speech_vecalign_b200.seg_align metadata.tsv out --src_lang en --tgt_lang de \\
+        --seg_dir segments --concat_dir cat_segs --embed_dir embeds --is_stopes_embed -a 6
+"""
+import argparse
+import logging
+import os
+import zlib
+from pathlib import Path
+
+import numpy as np
+
+from . import embedding_utils as eu
+from .dp_utils import vecalign_batch
+from .engine import records_to_alignments
+from .vecalign import load_ignore_index_file, make_alignment_types, print_alignments, width_over2_for
+
+logger = logging.getLogger("seg_align")
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    p.add_argument("metadata", help="tab-separated pairs of audio paths, one pair per line")
+    p.add_argument("out_dir", help="alignments are written to out_dir/<src_lang>-<tgt_lang>/")
+    p.add_argument("--src_lang", required=True)
+    p.add_argument("--tgt_lang", required=True)
+    p.add_argument("--seg_dir", required=True, help="raw segment lists")
+    p.add_argument("--concat_dir", required=True, help="concatenated-segment lists (embedding row keys)")
+    p.add_argument("--embed_dir", required=True, help="embedding files")
+    p.add_argument("--is_stopes_embed", action="store_true", help=".embed files written by stopes (.npy framed)")
+    p.add_argument("--fp16_embed", action="store_true", help="raw fp16 dumps (SONAR / numpy)")
+    p.add_argument("-a", "--alignment_max_size", type=int, default=6)
+    p.add_argument("--search_buffer_size", type=int, default=5)
+    p.add_argument("-d", "--del_percentile_frac", type=float, default=0.2)
+    p.add_argument("--max_size_full_dp", type=int, default=300)
+    p.add_argument("--costs_sample_size", type=int, default=20000)
+    p.add_argument("--num_samps_for_norm", type=int, default=100)
+    p.add_argument("--ign_indices_dir", default=None)
+    # execution
+    p.add_argument("--batch_gb", type=float, default=16.0, help="embedding bytes per GPU batch")
+    p.add_argument("--skip_existing", action="store_true")
+    p.add_argument("--seed", type=int, default=0)
+    p.add_argument("--cost_mode", default="exact", choices=["exact", "fast", "tc"])
+    p.add_argument("--rank", type=int, default=None, help="shard index (default: RANK env, else 0)")
+    p.add_argument("--n_shard", type=int, default=None, help="number of shards (default: WORLD_SIZE env, else 1)")
+    return p
+
+
+def _existing(path, what):
+    if path.exists():
+        return True
+    logger.warning("%s does not exist (%s); pair skipped", path, what)
+    return False
+
+
+def resolve_pairs(meta_lines, args):
+    """metadata line -> dict of the files step 5.4 needs; pairs with a missing file are dropped with
+    a warning, exactly the cases align.py:117-179 drops."""
+    sl, tl = args.src_lang, args.tgt_lang
+    out_dir = Path(args.out_dir) / f"{sl}-{tl}"
+    ign_dir = Path(args.ign_indices_dir) / f"{sl}-{tl}" if args.ign_indices_dir else None
+    jobs = []
+    for line in meta_lines:
+        line = line.strip()
+        if not line:
+            continue
+        src_audio, tgt_audio = line.split("\t")[:2]
+        s, t = Path(src_audio), Path(tgt_audio)
+        item = {"out": out_dir / f"{s.stem}-{t.stem}.txt"}
+        ok = True
+        for key, root, suffix in (("seg", args.seg_dir, ".txt"), ("cat", args.concat_dir, ".txt"), ("emb", args.embed_dir, ".embed")):
+            item["src_" + key] = (Path(root) / sl / s.name).with_suffix(suffix)
+            item["tgt_" + key] = (Path(root) / tl / t.name).with_suffix(suffix)
+            ok = ok and _existing(item["src_" + key], key) and _existing(item["tgt_" + key], key)
+            if not ok:
+                break
+        if not ok:
+            continue
+        for side in ("src", "tgt"):
+            f = ign_dir / f"{s.stem}-{t.stem}.{side}.txt" if ign_dir else None
+            item[side + "_ign"] = f if f is not None and f.exists() else None
+        jobs.append(item)
+    return out_dir, jobs
+
+
+def _count_lines(path):
+    with open(path, "rb") as f:
+        return sum(1 for _ in f)
+
+
+def load_pair(item, k, args):
+    """(vecs0, vecs1) as make_doc_embedding builds them (utils/embedding_utils.py:135-203)."""
+    out = []
+    for side in ("src", "tgt"):
+        key_to_row, rows = eu.read_in_embeddings(str(item[side + "_cat"]), str(item[side + "_emb"]),
+                                                 args.is_stopes_embed, args.fp16_embed)
+        lines = open(item[side + "_seg"], "rt", encoding="utf-8").readlines()
+        ign = load_ignore_index_file(item[side + "_ign"]) if item[side + "_ign"] else None
+        out.append(eu.make_doc_embedding(key_to_row, rows, lines, k, ignore_indices=ign, overlap_segments=True))
+    return out[0], out[1]
+
+
+def pair_seed(item, seed):
+    return (zlib.crc32(item["out"].name.encode()) ^ (seed & 0xFFFFFFFF)) & 0xFFFFFFFF
+
+
+def run(args):
+    from .sharding import estimate_work, lpt_partition
+    rank = args.rank if args.rank is not None else int(os.environ.get("RANK", "0"))
+    nshard = args.n_shard if args.n_shard is not None else int(os.environ.get("WORLD_SIZE", "1"))
+    assert 0 <= rank < nshard, f"invalid rank/n_shard {rank}/{nshard}"
+    if "LOCAL_RANK" in os.environ:
+        import torch
+        torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+
+    a = max(2, args.alignment_max_size)                           # vecalign.py:230-232
+    k = a - 1
+    types = make_alignment_types(a)
+    w = width_over2_for(k, k, args.search_buffer_size)
+    out_dir, jobs = resolve_pairs(open(args.metadata, "rt", encoding="utf-8"), args)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    if args.skip_existing:
+        jobs = [j for j in jobs if not j["out"].exists()]
+    sizes = [(_count_lines(j["src_seg"]), _count_lines(j["tgt_seg"])) for j in jobs]
+    if nshard > 1 and jobs:
+        mine = lpt_partition(estimate_work([s[0] for s in sizes], [s[1] for s in sizes], a, args.search_buffer_size), nshard)[rank]
+        jobs, sizes = [jobs[i] for i in mine], [sizes[i] for i in mine]
+    logger.info("shard %d/%d: %d document pairs", rank, nshard, len(jobs))
+
+    budget = args.batch_gb * 2 ** 30
+    done, i = 0, 0
+    while i < len(jobs):
+        batch, used = [], 0.0
+        while i < len(jobs) and (not batch or used + k * sum(sizes[i]) * eu.EMBED_DIM * 4 <= budget):
+            used += k * sum(sizes[i]) * eu.EMBED_DIM * 4
+            batch.append(jobs[i])
+            i += 1
+        pairs = [load_pair(item, k, args) for item in batch]
+        res = vecalign_batch(pairs, types, args.del_percentile_frac, w, args.max_size_full_dp, args.costs_sample_size,
+                             args.num_samps_for_norm, cost_mode=args.cost_mode, output="records",
+                             seeds=[pair_seed(item, args.seed) for item in batch])
+        for item, r in zip(batch, res):
+            al, sc = records_to_alignments(r["recs"])
+            tmp = item["out"].with_suffix(".txt.tmp")
+            with open(tmp, "w") as f:
+                print_alignments(al, scores=sc, ofile=f)
+            os.replace(tmp, item["out"])
+        done += len(batch)
+        logger.info("shard %d: %d/%d pairs aligned", rank, done, len(jobs))
+    return done
+
+
+def main(argv=None):
+    logging.basicConfig(level=os.environ.get("LOGLEVEL", "INFO"))
+    args = build_parser().parse_args(argv)
+    logger.info(args)
+    return run(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,69 @@
+"""The batch driver that replaces svecalign/seg_align/align.py: file
+resolution and sharding on the CPU, and one real run over the shipped example on the GPU."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, same_alignments
+
+NAME = "20180313-0900-PLENARY-15"
+
+
+def _tree(tmp_path, with_ignore=True, break_one=False):
+    ex = os.path.join(GOLDEN, "example")
+    for lang in ("en", "de"):
+        for sub, src, suffix in (("segments", f"{lang}.segments.txt", ".txt"), ("cat_segs", f"{lang}.cat_segs.txt", ".txt"),
+                                 ("embeds", f"{lang}.embed", ".embed")):
+            d = tmp_path / sub / lang
+            d.mkdir(parents=True, exist_ok=True)
+            shutil.copy(os.path.join(ex, src), d / f"{NAME}_{lang}{suffix}")
+    if with_ignore:
+        d = tmp_path / "ign" / "en-de"
+        d.mkdir(parents=True)
+        shutil.copy(os.path.join(ex, "ignore.src.txt"), d / f"{NAME}_en-{NAME}_de.src.txt")
+        shutil.copy(os.path.join(ex, "ignore.tgt.txt"), d / f"{NAME}_en-{NAME}_de.tgt.txt")
+    meta = tmp_path / "metadata.tsv"
+    lines = [f"/audio/en/{NAME}_en.ogg\t/audio/de/{NAME}_de.ogg"]
+    if break_one:
+        lines.append("/audio/en/missing_en.ogg\t/audio/de/missing_de.ogg")
+    meta.write_text("\n".join(lines) + "\n")
+    argv = [str(meta), str(tmp_path / "out"), "--src_lang", "en", "--tgt_lang", "de", "--seg_dir", str(tmp_path / "segments"),
+            "--concat_dir", str(tmp_path / "cat_segs"), "--embed_dir", str(tmp_path / "embeds"), "--is_stopes_embed", "-a", "6"]
+    if with_ignore:
+        argv += ["--ign_indices_dir", str(tmp_path / "ign")]
+    return argv
+
+
+def test_resolve_pairs_and_seeds(tmp_path):
+    from speech_vecalign_b200 import seg_align
+    argv = _tree(tmp_path, break_one=True)
+    args = seg_align.build_parser().parse_args(argv)
+    assert args.alignment_max_size == 6 and args.search_buffer_size == 5 and args.del_percentile_frac == 0.2
+    assert args.max_size_full_dp == 300 and args.costs_sample_size == 20000 and args.num_samps_for_norm == 100
+    out_dir, jobs = seg_align.resolve_pairs(open(args.metadata), args)
+    assert out_dir.name == "en-de" and len(jobs) == 1                 # the pair with missing files is dropped
+    j = jobs[0]
+    assert j["out"].name == f"{NAME}_en-{NAME}_de.txt"
+    assert j["src_emb"].name == f"{NAME}_en.embed" and j["tgt_cat"].name == f"{NAME}_de.txt"
+    assert j["src_ign"] is not None and j["tgt_ign"] is not None
+    assert seg_align.pair_seed(j, 0) == seg_align.pair_seed(j, 0) != seg_align.pair_seed(j, 1)
+    v0, v1 = seg_align.load_pair(j, 5, args)
+    assert v0.shape == (5, 237, 1024) and v1.shape == (5, 217, 1024) and v0.dtype == np.float32
+
+
+@pytest.mark.gpu
+def test_driver_reproduces_shipped_alignment(tmp_path):
+    from speech_vecalign_b200 import seg_align
+    from speech_vecalign_b200.vecalign import read_alignments
+    argv = _tree(tmp_path)
+    assert seg_align.main(argv) == 1
+    out = tmp_path / "out" / "en-de" / f"{NAME}_en-{NAME}_de.txt"
+    got = read_alignments(str(out))
+    shipped = os.path.join(GOLDEN, "example", "shipped_alignment_a6.txt")
+    assert same_alignments(got, read_alignments(shipped))
+    scores = [float(ln.rsplit(":", 1)[1]) for ln in open(out)]
+    ref = [float(ln.rsplit(":", 1)[1]) for ln in open(shipped)]
+    assert np.max(np.abs(np.array(scores) - np.array(ref))) <= 0.05      # other RNG state
+    assert seg_align.main(argv + ["--skip_existing"]) == 0
