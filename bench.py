@@ -382,13 +382,31 @@ def run_ours(args):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
     except Exception:
         pass
+    # what bounds each launcher: the cost kernels are FP32-pipe / shared-memory bound (arithmetic
+    # intensity 17-36 flop/B, exact mode = separate multiply and add, no FMA), the DPs are serial latency chains
+    BOUND = {"svx_level_prologue": "hbm", "svx_normalize_rows": "hbm", "svx_downsample": "hbm", "svx_sample_norms": "hbm",
+             "svx_score_pairs": "l2-gather", "svx_del_knob": "latency", "svx_dense_costs": "fp32" if args.cost_mode != "tc" else "tensor",
+             "svx_dense_dp": "latency", "svx_banded_costs_level0": "fp32", "svx_banded_costs_coarse": "smem",
+             "svx_banded_dp_level0": "latency", "svx_banded_dp_coarse": "latency"}
+    flops = run.cost_flops()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * sm_mhz * 1e6 * (1 if args.cost_mode == "exact" else 2) / 1e12     # TFLOP/s: mul and add issue separately in exact mode
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg.get(dom, 0), "ms_per_launch": dom_ms,
-                "share_of_step": ktimes[dom] / max(serial_ms, 1e-9),
+                "share_of_step": ktimes[dom] / max(serial_ms, 1e-9), "limiter": BOUND.get(dom, "hbm"),
                 "timing": f"CUDA events around every launcher, {kpasses} extra passes of the same step as one serial chain"}
-    kernels = {nm: {"ms_per_step": ms, "GBps": (alg.get(nm, 0) / (ms * 1e-3) / 1e9) if ms > 0 else None}
-               for nm, ms in sorted(ktimes.items(), key=lambda kv: -kv[1])}
+    if dom in flops and dom_ms > 0:
+        tf = flops[dom] / (dom_ms * 1e-3) / 1e12
+        roofline["fp32"] = {"achieved_tflops": tf, "peak_tflops": fp32_peak, "frac": tf / fp32_peak,
+                            "peak_source": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz, " +
+                                           ("1 flop/instr (exact mode: __fmul_rn + __fadd_rn, no FMA)" if args.cost_mode == "exact" else "FMA")}
+    kernels = {}
+    for nm, ms in sorted(ktimes.items(), key=lambda kv: -kv[1]):
+        gbps = (alg.get(nm, 0) / (ms * 1e-3) / 1e9) if ms > 0 else None
+        kernels[nm] = {"ms_per_step": ms, "GBps": gbps, "hbm_frac": (gbps / hbm_peak) if gbps else None, "limiter": BOUND.get(nm)}
+        if nm in flops and ms > 0:
+            kernels[nm]["fp32_tflops"] = flops[nm] / (ms * 1e-3) / 1e12
 
     # ---- parity spot check against the oracle (outside every timed region) -----------------------
     parity = None

@@ -104,6 +104,23 @@ typedef struct SvxNormJob {
 SVX_API int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs_h, int njobs, int dim, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Overlap tensor on the device: replaces the copy loop of make_doc_embedding
+ * (utils/embedding_utils.py:135-203).  out[j, e, :] = rows[table[j, e]] widened to fp32, a zero row
+ * for table < 0 (PAD, unknown key, ignored concatenation, position before the document start) and
+ * for source rows that contain a NaN (the reference zeroes those, :196-200).  `rows` is the content
+ * of the .embed file in its on-disk dtype (fp16 for SpeechLASER / SONAR dumps), so the host->device
+ * transfer is the file, not the K-fold expanded fp32 tensor.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxGatherJob {
+    const void *rows;        /* (nrows, dim) fp16 or fp32                                  */
+    const int32_t *table;    /* (k, n) source row of every (overlap, position), -1 = zeros */
+    float *out;              /* (k, n, dim) fp32                                           */
+    int32_t *nan_rows;       /* (1) or NULL: number of output rows zeroed because of NaNs  */
+    int32_t k, n, nrows, is_fp16;
+} SvxGatherJob;
+SVX_API int svx_gather_doc_embedding(const SvxGatherJob *jobs_d, const SvxGatherJob *jobs_h, int njobs, int dim, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused level prologue: everything dp_utils.vecalign does to one side of one level before the
  * costs (dp_utils.py:396-397, 416-418, 423-444), in the fewest passes over HBM:
  *   (1) mean   [levels >= 1]  per-overlap mean row of the un-centred pair sums (np.mean axis=0 order)
@@ -126,6 +143,9 @@ typedef struct SvxLevelJob {
     double *mbar;            /* (dim + 1024) scratch: mean sample vector, then 2048 fp32 denominators     */
     float *norms;            /* (k, n) output, or NULL                                                    */
     int32_t k, n, ko, no, per;
+    int32_t keep;            /* overlaps [0, keep) get their finished rows and norms stored; the others
+                                are only normalised on the fly for the pair sums (levels >= 1 align
+                                1-1 only: overlap 0 is all the later kernels read).  keep = k stores all. */
 } SvxLevelJob;
 SVX_API int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *jobs_h, int njobs, int dim, void *stream);
 
@@ -269,7 +289,7 @@ SVX_API int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long long n
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);
 SVX_API long long svx_launch_count(int reset); /* kernels launched since the last reset */
-SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec,7 Level */
+SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec,7 Level,8 Gather */
 
 #ifdef __cplusplus
 }

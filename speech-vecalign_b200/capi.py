@@ -30,7 +30,10 @@ NORM = np.dtype([("vecs", _P), ("other", _P), ("idx", _P), ("mbar", _P), ("norms
                 align=True)
 LEVEL = np.dtype([("vecs", _P), ("mean", _P), ("next", _P), ("other", _P), ("other_mean", _P), ("idx", _P),
                   ("mbar", _P), ("norms", _P),
-                  ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32)], align=True)
+                  ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32),
+                  ("keep", np.int32)], align=True)
+GATHER = np.dtype([("rows", _P), ("table", _P), ("out", _P), ("nan_rows", _P),
+                   ("k", np.int32), ("n", np.int32), ("nrows", np.int32), ("is_fp16", np.int32)], align=True)
 SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
                   ("scores", _P), ("del_penalty", _P), ("perm", _P), ("dots", _P),
                   ("ne", np.int32), ("nf", np.int32), ("nsamp", np.int32)], align=True)
@@ -49,7 +52,7 @@ BAND = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("ypath", _P), 
                  ("xo", np.int8, (SVX_MAX_TYPES,)), ("yo", np.int8, (SVX_MAX_TYPES,)),
                  ("amax", np.int16)], align=True)
 
-_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL]
+_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER]
 
 _lib = None
 
@@ -84,6 +87,7 @@ def lib():
         "svx_downsample": [vp, vp, ci, ci, vp],
         "svx_sample_norms": [vp, vp, ci, ci, vp],
         "svx_level_prologue": [vp, vp, ci, ci, vp],
+        "svx_gather_doc_embedding": [vp, vp, ci, ci, vp],
         "svx_score_pairs": [vp, vp, ci, ci, ci, vp],
         "svx_del_knob": [vp, vp, ci, cd, vp],
         "svx_host_del_knob": [vp, ci, cd, vp],
@@ -118,7 +122,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = [
-    "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_level_prologue", "svx_score_pairs", "svx_del_knob",
+    "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_level_prologue", "svx_gather_doc_embedding", "svx_score_pairs", "svx_del_knob",
     "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_dense_tmaps_encode", "svx_path_len", "svx_banded_costs",
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_host_randint_stream",
     "svx_host_randint_seeded", "svx_upload_pinned", "svx_version",

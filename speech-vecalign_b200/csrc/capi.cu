@@ -37,6 +37,7 @@ extern "C" int svx_sizeof_job(int which)
         case 5: return (int)sizeof(SvxBandJob);
         case 6: return (int)sizeof(SvxAlignRec);
         case 7: return (int)sizeof(SvxLevelJob);
+        case 8: return (int)sizeof(SvxGatherJob);
         default: return -1;
     }
 }

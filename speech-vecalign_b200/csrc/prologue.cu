@@ -8,6 +8,7 @@
 // Row kernels use one warp per 4 KB embedding row: eight coalesced 16-byte loads per lane
 // (one 128-float numpy "pairwise block" per load step), the numpy pairwise-sum tree is then
 // replayed exactly through a padded, bank-conflict-free shared-memory transpose.
+#include <cuda_fp16.h>
 #include "svx_common.cuh"
 
 namespace {
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) k_level_finish(const Svx
                 }
             }
             warp_unit_row<DIM>(v[r], scratch[warp], lane);
+            if (o >= job.keep) continue;       // only feeds the pair sum below
 #pragma unroll
             for (int b = 0; b < NB; ++b) *reinterpret_cast<float4 *>(q + b * 128 + 4 * lane) = v[r][b];
             if (want_norms) {
@@ -763,5 +765,71 @@ extern "C" int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long lon
     if (grid > 148 * 4) grid = 148 * 4;
     k_upload<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<uint4 *>(dst_d), reinterpret_cast<const uint4 *>(src_pinned_h), n16);
     SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// svx_gather_doc_embedding: a warp per output row; the source row (2 KB fp16 or 4 KB fp32) is read
+// with 16-byte loads, checked for NaNs with a warp vote, widened and written as fp32.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_gather_rows(const SvxGatherJob *jobs, int dim)
+{
+    const SvxGatherJob job = jobs[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t total = (int64_t)job.k * job.n;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < total; r += (int64_t)gridDim.x * 8) {
+        const int src = job.table[r];
+        float *dst = job.out + r * dim;
+        const bool have = src >= 0 && src < job.nrows;
+        bool bad = false;
+        for (int d0 = 0; d0 < dim; d0 += 256) {              // 32 lanes x 8 elements
+            const int d = d0 + 8 * lane;
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = 0.0f;
+            if (have && d < dim) {
+                if (job.is_fp16) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(job.rows) + (size_t)src * dim + d));
+                    const __half2 *h = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const float2 f = __half22float2(h[u]); v[2 * u] = f.x; v[2 * u + 1] = f.y; }
+                } else {
+                    const float *p = reinterpret_cast<const float *>(job.rows) + (size_t)src * dim + d;
+                    const float4 a = ldg_f4(p), b = ldg_f4(p + 4);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) bad |= (v[u] != v[u]);
+            }
+            if (d < dim) {
+                *reinterpret_cast<float4 *>(dst + d) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(dst + d + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) {                  // embedding_utils.py:196-200: reset to zero
+            for (int d = 4 * lane; d < dim; d += 128) *reinterpret_cast<float4 *>(dst + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == 0 && job.nan_rows) atomicAdd(job.nan_rows, 1);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int svx_gather_doc_embedding(const SvxGatherJob *jobs_d, const SvxGatherJob *jobs_h, int njobs, int dim, void *stream)
+{
+    SVX_REQUIRE(dim > 0 && dim % 8 == 0, SVX_ERR_UNSUPPORTED, "svx_gather_doc_embedding: dim %d must be a multiple of 8", dim);
+    if (njobs <= 0) return SVX_OK;
+    for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
+        const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
+        int64_t mr = 0;
+        for (int j = 0; j < nj; ++j) {
+            const int64_t r = (int64_t)jobs_h[j0 + j].k * jobs_h[j0 + j].n;
+            if (r > mr) mr = r;
+        }
+        if (mr == 0) continue;
+        dim3 grid(rows_grid(mr), nj);
+        k_gather_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(jobs_d + j0, dim);
+        SVX_LAUNCH_CHECK();
+    }
     return SVX_OK;
 }

@@ -114,3 +114,70 @@ def make_doc_embedding(sent2id: dict, line_embeddings: np.ndarray, lines: List[s
         rows[bad] = 0.0
     vecs[hit] = rows
     return vecs
+
+
+# ---------------------------------------------------------------------------------------------
+# Device path: the .embed rows travel in their on-disk dtype and the (K, N, D)
+# fp32 overlap tensor is gathered on the GPU.
+# ---------------------------------------------------------------------------------------------
+def load_embedding_rows(embed_file: str, use_stopes: bool = False, fp16_embed: bool = False) -> np.ndarray:
+    """The rows of an .embed file WITHOUT widening: (rows, EMBED_DIM) float16 or float32
+    (same files as load_sent_embeddings, embedding_utils.py:38-76)."""
+    if use_stopes:
+        try:
+            from stopes.utils.embedding_utils import Embedding  # noqa
+            with Embedding(embed_file).open_for_read("mmap") as e:
+                emb = np.asarray(e)
+        except ImportError:
+            emb = np.load(embed_file, mmap_mode="r")
+    else:
+        emb = np.fromfile(embed_file, dtype=np.float16 if fp16_embed else np.float32, count=-1)
+        if emb.size == 0:
+            raise Exception('Got empty embedding file')
+        emb = emb.reshape(emb.shape[0] // EMBED_DIM, EMBED_DIM)
+    if emb.dtype not in (np.float16, np.float32):
+        emb = emb.astype(np.float32)
+    return emb
+
+
+def read_in_embedding_rows(text_file: str, embed_file: str, use_stopes: bool = False, fp16_embed: bool = False):
+    """read_in_embeddings (embedding_utils.py:79-103) keeping the on-disk dtype of the rows."""
+    sent2line: Dict[str, int] = {}
+    with open(text_file, 'rt', encoding="utf-8") as fin:
+        for i, line in enumerate(fin):
+            sent2line.setdefault(line.strip(), i)
+    return sent2line, load_embedding_rows(embed_file, use_stopes, fp16_embed)
+
+
+def make_doc_embedding_device(sent2id: dict, rows: np.ndarray, lines: List[str], max_overlaps: int,
+                              ignore_indices: Optional[Set[Tuple[int, int]]] = None, overlap_segments: bool = False,
+                              device=None):
+    """make_doc_embedding (embedding_utils.py:135-203) with the copy loop on the GPU: uploads `rows`
+    (fp16 or fp32, as stored) and the (K, N) row table, returns the (K, N, D) fp32 CUDA tensor —
+    bit-identical to the host function (fp16 -> fp32 is exact; NaN rows, PAD, unknown keys -> zeros)."""
+    import torch
+    from . import capi
+    if not torch.cuda.is_available():
+        raise capi.SvxError("no CUDA device: speech_vecalign_b200 has no CPU fallback")
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    table = overlap_row_table(sent2id, lines, max_overlaps, ignore_indices, overlap_segments)
+    k, n = table.shape
+    rows = np.ascontiguousarray(rows)
+    if rows.dtype not in (np.float16, np.float32) or rows.ndim != 2:
+        raise ValueError("rows must be a (nrows, dim) float16 or float32 array")
+    dim = rows.shape[1]
+    t_rows = torch.from_numpy(rows).to(dev, non_blocking=True)
+    t_tab = torch.from_numpy(np.ascontiguousarray(table)).to(dev, non_blocking=True)
+    out = torch.empty((k, n, dim), dtype=torch.float32, device=dev)
+    nan_rows = torch.zeros(1, dtype=torch.int32, device=dev)
+    if k * n:
+        job = np.zeros(1, dtype=capi.GATHER)
+        job["rows"], job["table"], job["out"], job["nan_rows"] = t_rows.data_ptr(), t_tab.data_ptr(), out.data_ptr(), nan_rows.data_ptr()
+        job["k"], job["n"], job["nrows"], job["is_fp16"] = k, n, rows.shape[0], int(rows.dtype == np.float16)
+        jd = torch.from_numpy(job.view(np.uint8).reshape(-1).copy()).to(dev)
+        capi.check(capi.lib().svx_gather_doc_embedding(jd.data_ptr(), capi.hptr(job), 1, dim,
+                                                       torch.cuda.current_stream(dev).cuda_stream), "svx_gather_doc_embedding")
+        bad = int(nan_rows.item())                        # also orders the kernel before t_rows / t_tab are released
+        if bad:
+            logger.error("loaded %d vector(s) with nan values; reset to zero", bad)
+    return out

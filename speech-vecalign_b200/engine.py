@@ -371,6 +371,8 @@ class BatchRun:
                 v["norms"] = np.where(want[sel], ptr(norms_k)[sel], 0)
                 v["mbar"] = ptr(mbar_k)[sel]
                 v["k"], v["n"], v["ko"], v["no"], v["per"] = ka, sa[sel], kb, sb[sel], per
+                # levels >= 1 align 1-1 only: later kernels read overlap 0 (debug keeps everything)
+                v["keep"] = ka if (lvl == 0 or keep_dense_csum) else min(1, ka)
             self.level_jobs.append((lj, np.repeat(rp[sel], 2)))
         nj_pair = np.concatenate([rp[sel0], rp[sel1]])
         order = np.argsort(nj_pair, kind="stable")       # pair-major so that a pair range is a job range
@@ -601,7 +603,8 @@ class BatchRun:
         for lj, _ in self.level_jobs:
             kk, nn = lj["k"].astype(np.int64), lj["n"].astype(np.int64)
             rows = kk * nn * D * 4
-            lvl_bytes += int((rows * (2 + (lj["mean"] != 0)) + (lj["next"] != 0) * kk * (nn // 2) * D * 4 + kk * nn * 4 +
+            kept = lj["keep"].astype(np.int64) * nn * D * 4
+            lvl_bytes += int((rows * (1 + (lj["mean"] != 0)) + kept + (lj["next"] != 0) * kk * (nn // 2) * D * 4 + kk * nn * 4 +
                               (lj["idx"] != 0) * lj["ko"].astype(np.int64) * lj["per"] * D * 4 * 2).sum())
         out = {
             "svx_level_prologue": lvl_bytes,
@@ -619,6 +622,18 @@ class BatchRun:
             "svx_banded_dp_coarse": int(((A[band_co] + 2) * B * (4 + 9)).sum()),
         }
         return out
+
+    def cost_flops(self):
+        """Algorithmic FLOPs of the cost launchers (2*D per dot product)."""
+        D, B = self.dim, self.band
+        l0 = self.rec_level == 0
+        top = self.rec_level == self.depth[self.rec_pair]
+        band_l0, band_co = self.banded & l0, self.banded & ~l0
+        return {
+            "svx_banded_costs_level0": int(2 * D * (self.T[band_l0] * self.A[band_l0] * B).sum()),
+            "svx_banded_costs_coarse": int(2 * D * (self.A[band_co] * B).sum()),
+            "svx_dense_costs": int(2 * D * (self.rs0[top] * self.rs1[top]).sum()),
+        }
 
     def dp_cells(self):
         """DP cells of the batch: banded nodes (A+2)*B per banded level plus the

@@ -57,6 +57,8 @@ def build_parser():
     # execution
     p.add_argument("--batch_gb", type=float, default=16.0, help="embedding bytes per GPU batch")
     p.add_argument("--skip_existing", action="store_true")
+    p.add_argument("--host_gather", action="store_true", help="build the overlap tensors on the host (reference path) "
+                                                             "instead of uploading the .embed rows and gathering on the GPU")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cost_mode", default="exact", choices=["exact", "fast", "tc"])
     p.add_argument("--rank", type=int, default=None, help="shard index (default: RANK env, else 0)")
@@ -106,15 +108,22 @@ def _count_lines(path):
         return sum(1 for _ in f)
 
 
-def load_pair(item, k, args):
-    """(vecs0, vecs1) as make_doc_embedding builds them (utils/embedding_utils.py:135-203)."""
+def load_pair(item, k, args, on_device=False):
+    """(vecs0, vecs1) as make_doc_embedding builds them (utils/embedding_utils.py:135-203).  on_device:
+    the .embed rows are uploaded in their on-disk dtype (fp16 for SpeechLASER/SONAR dumps) and the (K, N, D)
+    tensor is gathered on the GPU — the host->device bytes are the file, not the K-fold fp32 expansion."""
     out = []
     for side in ("src", "tgt"):
-        key_to_row, rows = eu.read_in_embeddings(str(item[side + "_cat"]), str(item[side + "_emb"]),
-                                                 args.is_stopes_embed, args.fp16_embed)
         lines = open(item[side + "_seg"], "rt", encoding="utf-8").readlines()
         ign = load_ignore_index_file(item[side + "_ign"]) if item[side + "_ign"] else None
-        out.append(eu.make_doc_embedding(key_to_row, rows, lines, k, ignore_indices=ign, overlap_segments=True))
+        if on_device:
+            key_to_row, rows = eu.read_in_embedding_rows(str(item[side + "_cat"]), str(item[side + "_emb"]),
+                                                         args.is_stopes_embed, args.fp16_embed)
+            out.append(eu.make_doc_embedding_device(key_to_row, rows, lines, k, ignore_indices=ign, overlap_segments=True))
+        else:
+            key_to_row, rows = eu.read_in_embeddings(str(item[side + "_cat"]), str(item[side + "_emb"]),
+                                                     args.is_stopes_embed, args.fp16_embed)
+            out.append(eu.make_doc_embedding(key_to_row, rows, lines, k, ignore_indices=ign, overlap_segments=True))
     return out[0], out[1]
 
 
@@ -153,7 +162,7 @@ def run(args):
             used += k * sum(sizes[i]) * eu.EMBED_DIM * 4
             batch.append(jobs[i])
             i += 1
-        pairs = [load_pair(item, k, args) for item in batch]
+        pairs = [load_pair(item, k, args, on_device=not args.host_gather) for item in batch]
         res = vecalign_batch(pairs, types, args.del_percentile_frac, w, args.max_size_full_dp, args.costs_sample_size,
                              args.num_samps_for_norm, cost_mode=args.cost_mode, output="records",
                              seeds=[pair_seed(item, args.seed) for item in batch])

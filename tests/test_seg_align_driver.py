@@ -67,3 +67,36 @@ def test_driver_reproduces_shipped_alignment(tmp_path):
     ref = [float(ln.rsplit(":", 1)[1]) for ln in open(shipped)]
     assert np.max(np.abs(np.array(scores) - np.array(ref))) <= 0.05      # other RNG state
     assert seg_align.main(argv + ["--skip_existing"]) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_device_gather_equals_make_doc_embedding(svb, dtype):
+    """svx_gather_doc_embedding == make_doc_embedding (utils/embedding_utils.py:135-203) bit for bit:
+    shipped example with its ignore indices, plus NaN rows and unknown keys."""
+    from speech_vecalign_b200 import embedding_utils as eu
+    from speech_vecalign_b200.vecalign import load_ignore_index_file
+    ex = os.path.join(GOLDEN, "example")
+    sent2id, rows = eu.read_in_embedding_rows(f"{ex}/en.cat_segs.txt", f"{ex}/en.embed", use_stopes=True)
+    assert rows.dtype == np.float16
+    rows = np.array(rows, dtype=dtype)
+    rows[7, 100] = np.nan                                  # a NaN row must come out as zeros
+    lines = open(f"{ex}/en.segments.txt").readlines()
+    ign = load_ignore_index_file(f"{ex}/ignore.src.txt")
+    sent2id.pop(next(iter(sent2id)))                       # an unknown key -> zero row
+    for k in (1, 3, 5):
+        ref = eu.make_doc_embedding(sent2id, rows.astype(np.float32), lines, k, ignore_indices=ign, overlap_segments=True)
+        got = eu.make_doc_embedding_device(sent2id, rows, lines, k, ignore_indices=ign, overlap_segments=True)
+        assert got.shape == ref.shape and np.array_equal(got.cpu().numpy(), ref)
+
+
+@pytest.mark.gpu
+def test_driver_host_and_device_gather_agree(tmp_path):
+    from speech_vecalign_b200 import seg_align
+    argv = _tree(tmp_path)
+    assert seg_align.main(argv) == 1
+    out = tmp_path / "out" / "en-de" / f"{NAME}_en-{NAME}_de.txt"
+    dev_txt = out.read_text()
+    out.unlink()
+    assert seg_align.main(argv + ["--host_gather"]) == 1
+    assert out.read_text() == dev_txt
