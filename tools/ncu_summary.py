@@ -49,6 +49,13 @@ def launches(path, out, traffic=None, workload="cfg2"):
         if len(r) > vi:
             per.setdefault(r[ii], {"k": r[ki]})[r[mi]] = float(r[vi].replace(",", ""))
     ls = list(per.values())
+    # keep the last COMPLETE step of the capture: a step starts with the level-0 prologue (first prologue
+    # kernel after a banded DP / upload / the start of the list) and ends with the level-0 banded DP
+    starts = [i for i, d in enumerate(ls) if "k_level_" in d["k"] and (i == 0 or "k_banded_dp" in ls[i - 1]["k"] or "k_upload" in ls[i - 1]["k"])]
+    ends = [i for i, d in enumerate(ls) if "k_banded_dp" in d["k"] and (i + 1 == len(ls) or "k_level_" in ls[i + 1]["k"])]
+    if starts and ends and any(s_ < ends[-1] for s_ in starts):
+        s_ = max(s_ for s_ in starts if s_ < ends[-1])
+        ls = ls[s_:ends[-1] + 1]
     # the last banded costs / dp launch of a step is level 0
     last_cost = max(i for i, d in enumerate(ls) if "k_banded_costs" in d["k"])
     last_dp = max(i for i, d in enumerate(ls) if "k_banded_dp" in d["k"])
