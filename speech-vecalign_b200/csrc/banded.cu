@@ -3,6 +3,7 @@
 //   svx_banded_costs (dp_core.pyx:165-267 make_sparse_costs)
 //   svx_banded_dp    (dp_core.pyx:269-404 sparse_dp; dp_utils.py:89-143 sparse_traceback +
 //                     process_scores; dp_utils.py:177-275 path glue)
+#include <stdlib.h>
 #include <type_traits>
 #include "svx_common.cuh"
 #include "svx_dp.h"
@@ -190,6 +191,207 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Banded costs, register-blocked (standard type set, K <= 5).
+//
+// In the thread-per-cell kernel above every 4 multiply-adds of a type need 8 LDS.128 per K(K+1)/2
+// types: the shared-memory pipe, not the FP32 pipe, is the limit.  Here a thread owns a 2 x 2 block of
+// POSITIONS (xx in {2X, 2X+1}, yy in {2Y, 2Y+1}): the four cells lie on anti-diagonals 2e, 2e+1, 2e+1,
+// 2e+2 (e = X + Y), all inside or next to the band, and share their operand rows, so 4K LDS.128 feed
+// 4 x T accumulators - twice the arithmetic per shared-memory byte.  Blocks are independent of the
+// path's direction, so there is no divergence; a block-diagonal e needs at most B/2 + 2 blocks to
+// cover the band rows of its three diagonals, and every band cell belongs to exactly one block.
+// Rows are kept in shared memory as [even positions | odd positions], so consecutive threads
+// (Y+1: two positions further) read consecutive rows: conflict-free LDS.128.
+// Tiles span 30 anti-diagonals (the 2B-1 halo rows are amortised over twice as many diagonals).
+// ---------------------------------------------------------------------------------------------
+constexpr int kBlkTA = 30;      // 16 block-diagonals per tile (kBlkTA / 2 + 1): a quarter-warp = 8 consecutive block-diagonals
+
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(192, (K <= 4 ? 2 : 1))
+k_banded_costs_blk(const SvxBandJob *jobs, int dim)
+{
+    constexpr int T = K * (K + 1) / 2;
+    extern __shared__ __align__(16) float tile[];      // two slice buffers, then the row source table
+    const SvxBandJob &job = jobs[blockIdx.y];
+    const int A = job.a_len;
+    const int a0 = blockIdx.x * kBlkTA;
+    if (a0 >= A) return;
+    const int d_first = a0, d_last = min(a0 + kBlkTA, A) - 1;
+    const int B = job.band, w = job.width_over2;
+    const int s0 = job.s0, s1 = job.s1;
+    const int32_t *ypath = job.ypath;
+    const int tid = threadIdx.x;
+    const int nb = B / 2 + 2, ne = kBlkTA / 2 + 1;
+
+    // positions touched by the tile, rounded out to even / odd ends
+    const int bf = ypath[d_first] - w, bl = ypath[d_last] - w;
+    const int ylo = ((bf) >> 1) * 2, yhi = ((bl + B - 1) >> 1) * 2 + 1;
+    const int xlo = ((d_first - (bf + B - 1)) >> 1) * 2, xhi = ((d_last - bl) >> 1) * 2 + 1;
+    const int NX = xhi - xlo + 1, NY = yhi - ylo + 1, HX = NX >> 1, HY = NY >> 1;
+    const int nrows = K * (NX + NY);
+    const int rows_cap = K * (kBlkTA + 2 * B + 6);
+    const int buf_floats = rows_cap * kBS;
+    int *srcoff = reinterpret_cast<int *>(tile + 2 * buf_floats);        // float offset from v0 / v1, -1 = zero row
+
+    // row slot -> source: x rows first (overlap-major, [even | odd] positions), then y rows
+    for (int r = tid; r < nrows; r += blockDim.x) {
+        int off = -1;
+        if (r < K * NX) {
+            const int k = r / NX, p = r % NX;
+            const int seg = xlo + (p < HX ? 2 * p : 2 * (p - HX) + 1);
+            if (k < job.k0 && seg >= 0 && seg < s0) off = (int)(((size_t)k * s0 + seg) * dim);
+        } else {
+            const int r2 = r - K * NX;
+            const int k = r2 / NY, p = r2 % NY;
+            const int seg = ylo + (p < HY ? 2 * p : 2 * (p - HY) + 1);
+            if (k < job.k1 && seg >= 0 && seg < s1) off = (int)(((size_t)k * s1 + seg) * dim);
+        }
+        srcoff[r] = off;
+    }
+
+    // this thread's block.  Consecutive lanes = consecutive block-diagonals e at the same band slot yi:
+    // along e both X and Y advance by 0 or 1, so the 8 lanes of an LDS.128 phase read rows that are
+    // equal (broadcast) or consecutive - no bank conflicts.
+    static_assert(kBlkTA / 2 + 1 == 16, "thread mapping assumes 16 block-diagonals per tile");
+    const int ei = tid & 15, yi = tid >> 4;
+    const int e = a0 / 2 - 1 + ei;
+    const int dlo = max(2 * e, d_first), dhi = min(2 * e + 2, d_last);
+    bool active = yi < nb && dlo <= dhi;
+    int xx0 = 0, yy0 = 0;
+    unsigned inband = 0;               // bit (2j + i): cell (xx0 + i, yy0 + j) is a band cell of this tile
+    int bslot[4] = {0, 0, 0, 0};
+    if (active) {
+        const int Y = ((ypath[dlo] - w) >> 1) + yi;
+        yy0 = 2 * Y; xx0 = 2 * (e - Y);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int d = 2 * e + i + j;
+                if (d >= d_first && d <= d_last) {
+                    const int b = yy0 + j - (ypath[d] - w);
+                    if (b >= 0 && b < B) { inband |= 1u << (2 * j + i); bslot[2 * j + i] = b; }
+                }
+            }
+        active = inband != 0;
+    }
+    const int xs_even = (xx0 - xlo) >> 1, ys_even = (yy0 - ylo) >> 1;      // slot of the even position in its half
+
+    float acc[4][T];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int t = 0; t < T; ++t) acc[c][t] = 0.0f;
+
+    const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
+    const float *gv0 = job.v0, *gv1 = job.v1;
+    const int xrows = K * NX;
+    auto issue = [&](int sl) {
+        const unsigned buf = tile_u32 + (unsigned)((sl & 1) * buf_floats * (int)sizeof(float));
+        for (int f = tid; f < nrows * (kBC / 4); f += blockDim.x) {
+            const int row = f >> 3, c4 = f & 7;
+            const int off = srcoff[row];
+            const float *gp = (row < xrows ? gv0 : gv1) + (off < 0 ? 0 : off) + sl * kBC + 4 * c4;
+            const int nbytes = off < 0 ? 0 : 16;
+            const unsigned dst = buf + (unsigned)((row * kBS + 4 * c4) * (int)sizeof(float));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(nbytes));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+
+    const int slices = dim / kBC;
+    __syncthreads();                      // srcoff is complete
+    issue(0);
+    for (int sl = 0; sl < slices; ++sl) {
+        if (sl + 1 < slices) {
+            issue(sl + 1);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
+        __syncthreads();
+        if (active) {
+            const float *buf = tile + (sl & 1) * buf_floats;
+            const float *px = buf + (size_t)xs_even * kBS;                       // even x position, overlap 0
+            const float *py = buf + (size_t)(xrows + ys_even) * kBS;
+#pragma unroll 2
+            for (int d = 0; d < kBC; d += 4) {
+                float4 xe[K], xo[K], ye[K], yo[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    xe[i] = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX) * kBS + d);
+                    xo[i] = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX + HX) * kBS + d);
+                    ye[i] = *reinterpret_cast<const float4 *>(py + (size_t)(i * NY) * kBS + d);
+                    yo[i] = *reinterpret_cast<const float4 *>(py + (size_t)(i * NY + HY) * kBS + d);
+                }
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+#pragma unroll
+                    for (int j = 0; i + j <= K - 1; ++j, ++t) {
+#define SVX_MAC4(ACC, XV, YV)                                                                       \
+    if (EXACT) {                                                                                    \
+        ACC = __fadd_rn(ACC, __fmul_rn(XV.x, YV.x)); ACC = __fadd_rn(ACC, __fmul_rn(XV.y, YV.y));   \
+        ACC = __fadd_rn(ACC, __fmul_rn(XV.z, YV.z)); ACC = __fadd_rn(ACC, __fmul_rn(XV.w, YV.w));   \
+    } else {                                                                                        \
+        ACC = fmaf(XV.x, YV.x, ACC); ACC = fmaf(XV.y, YV.y, ACC);                                   \
+        ACC = fmaf(XV.z, YV.z, ACC); ACC = fmaf(XV.w, YV.w, ACC);                                   \
+    }
+                        SVX_MAC4(acc[0][t], xe[i], ye[j])       // (xx0,     yy0)
+                        SVX_MAC4(acc[1][t], xo[i], ye[j])       // (xx0 + 1, yy0)
+                        SVX_MAC4(acc[2][t], xe[i], yo[j])       // (xx0,     yy0 + 1)
+                        SVX_MAC4(acc[3][t], xo[i], yo[j])       // (xx0 + 1, yy0 + 1)
+#undef SVX_MAC4
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!((inband >> c) & 1)) continue;
+        const int i = c & 1, j = c >> 1;
+        const int xx = xx0 + i, yy = yy0 + j, d = 2 * e + i + j;
+        const bool inside = xx >= 0 && xx < s0 && yy >= 0 && yy < s1;
+        float *out = job.costs + (size_t)d * T * B + bslot[c];
+        int t = 0;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int ky = 0; kx + ky <= K - 1; ++ky, ++t) {
+                float cst = INFINITY;
+                if (inside)
+                    cst = svx_band_cost(acc[c][t], kx + 1, ky + 1, job.n0[(size_t)kx * s0 + xx], job.n1[(size_t)ky * s1 + yy]);
+                out[(size_t)t * B] = cst;
+            }
+    }
+}
+
+template <int K>
+int launch_costs_blk(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, cudaStream_t st)
+{
+    const int nb = band / 2 + 2, ne = kBlkTA / 2 + 1;
+    const int threads = ((nb * ne + 31) / 32) * 32;
+    if (threads > 192) return -1;
+    const int rows_cap = K * (kBlkTA + 2 * band + 6);
+    const size_t smem = (size_t)2 * rows_cap * kBS * sizeof(float) + (size_t)rows_cap * sizeof(int);
+    if (smem > 200 * 1024) return -1;
+    dim3 grid((max_alen + kBlkTA - 1) / kBlkTA, nj);
+    if (mode == SVX_COST_EXACT) {
+        auto kern = k_banded_costs_blk<K, true>;
+        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim);
+    } else {
+        auto kern = k_banded_costs_blk<K, false>;
+        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim);
+    }
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -741,7 +943,17 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
     for (int jb0 = 0; jb0 < njobs; jb0 += SVX_MAX_GRID_Y) {
         const int nj = njobs - jb0 < SVX_MAX_GRID_Y ? njobs - jb0 : SVX_MAX_GRID_Y;
         int rc = -1;
-        if (standard) {
+        // SVX_COSTS_CELL=1 selects the thread-per-cell kernel also for K <= 5 (A/B measurements)
+        static const bool per_cell = getenv("SVX_COSTS_CELL") && atoi(getenv("SVX_COSTS_CELL")) != 0;
+        if (standard && !per_cell && K <= 5 && (j0.band & 1) == 0) {
+            switch (K) {
+#define CASE(KK) case KK: rc = launch_costs_blk<KK>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st); break;
+                CASE(1) CASE(2) CASE(3) CASE(4) CASE(5)
+#undef CASE
+                default: break;
+            }
+        }
+        if (rc == -1 && standard) {
             switch (K) {
 #define CASE(KK) case KK: rc = launch_costs<KK, KK, true>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st); break;
                 CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
