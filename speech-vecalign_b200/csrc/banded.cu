@@ -194,7 +194,7 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Banded costs, register-blocked (standard type set, K <= 5).
+// Banded costs, register-blocked (standard type set, K <= 4).
 //
 // In the thread-per-cell kernel above every 4 multiply-adds of a type need 8 LDS.128 per K(K+1)/2
 // types: the shared-memory pipe, not the FP32 pipe, is the limit.  Here a thread owns a 2 x 2 block of
@@ -210,7 +210,7 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
 constexpr int kBlkTA = 30;      // 16 block-diagonals per tile (kBlkTA / 2 + 1): a quarter-warp = 8 consecutive block-diagonals
 
 template <int K, bool EXACT>
-__global__ void __launch_bounds__(192, (K <= 4 ? 2 : 1))
+__global__ void __launch_bounds__(192, 2)
 k_banded_costs_blk(const SvxBandJob *jobs, int dim)
 {
     constexpr int T = K * (K + 1) / 2;
@@ -319,17 +319,18 @@ k_banded_costs_blk(const SvxBandJob *jobs, int dim)
             const float *py = buf + (size_t)(xrows + ys_even) * kBS;
 #pragma unroll 2
             for (int d = 0; d < kBC; d += 4) {
-                float4 xe[K], xo[K], ye[K], yo[K];
+                // y operands of every overlap stay live; x operands are fetched overlap by overlap
+                float4 ye[K], yo[K];
 #pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    xe[i] = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX) * kBS + d);
-                    xo[i] = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX + HX) * kBS + d);
-                    ye[i] = *reinterpret_cast<const float4 *>(py + (size_t)(i * NY) * kBS + d);
-                    yo[i] = *reinterpret_cast<const float4 *>(py + (size_t)(i * NY + HY) * kBS + d);
+                for (int j = 0; j < K; ++j) {
+                    ye[j] = *reinterpret_cast<const float4 *>(py + (size_t)(j * NY) * kBS + d);
+                    yo[j] = *reinterpret_cast<const float4 *>(py + (size_t)(j * NY + HY) * kBS + d);
                 }
                 int t = 0;
 #pragma unroll
-                for (int i = 0; i < K; ++i)
+                for (int i = 0; i < K; ++i) {
+                    const float4 xe = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX) * kBS + d);
+                    const float4 xo = *reinterpret_cast<const float4 *>(px + (size_t)(i * NX + HX) * kBS + d);
 #pragma unroll
                     for (int j = 0; i + j <= K - 1; ++j, ++t) {
 #define SVX_MAC4(ACC, XV, YV)                                                                       \
@@ -340,12 +341,13 @@ k_banded_costs_blk(const SvxBandJob *jobs, int dim)
         ACC = fmaf(XV.x, YV.x, ACC); ACC = fmaf(XV.y, YV.y, ACC);                                   \
         ACC = fmaf(XV.z, YV.z, ACC); ACC = fmaf(XV.w, YV.w, ACC);                                   \
     }
-                        SVX_MAC4(acc[0][t], xe[i], ye[j])       // (xx0,     yy0)
-                        SVX_MAC4(acc[1][t], xo[i], ye[j])       // (xx0 + 1, yy0)
-                        SVX_MAC4(acc[2][t], xe[i], yo[j])       // (xx0,     yy0 + 1)
-                        SVX_MAC4(acc[3][t], xo[i], yo[j])       // (xx0 + 1, yy0 + 1)
+                        SVX_MAC4(acc[0][t], xe, ye[j])       // (xx0,     yy0)
+                        SVX_MAC4(acc[1][t], xo, ye[j])       // (xx0 + 1, yy0)
+                        SVX_MAC4(acc[2][t], xe, yo[j])       // (xx0,     yy0 + 1)
+                        SVX_MAC4(acc[3][t], xo, yo[j])       // (xx0 + 1, yy0 + 1)
 #undef SVX_MAC4
                     }
+                }
             }
         }
         __syncthreads();
@@ -945,10 +947,12 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
         int rc = -1;
         // SVX_COSTS_CELL=1 selects the thread-per-cell kernel also for K <= 5 (A/B measurements)
         static const bool per_cell = getenv("SVX_COSTS_CELL") && atoi(getenv("SVX_COSTS_CELL")) != 0;
-        if (standard && !per_cell && K <= 5 && (j0.band & 1) == 0) {
+        // measured on B200: the register-blocked kernel wins for K <= 4 (cfg2: 18.1 -> 16.1 ms, coarse levels
+        // 3.6 -> 1.8 ms); at K = 5 (15 types, 60 accumulators per thread) the thread-per-cell kernel is faster
+        if (standard && !per_cell && K <= 4 && (j0.band & 1) == 0) {
             switch (K) {
 #define CASE(KK) case KK: rc = launch_costs_blk<KK>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st); break;
-                CASE(1) CASE(2) CASE(3) CASE(4) CASE(5)
+                CASE(1) CASE(2) CASE(3) CASE(4)
 #undef CASE
                 default: break;
             }
