@@ -10,12 +10,14 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// Dense costs: 32x32 output tile per CTA, 256 threads, 2x2 outputs per thread (rows t and t+16 so
-// that the 8 lanes of one LDS.128 phase hit 8 consecutive rows = 8 distinct bank groups with the
-// 68-float row stride).  Each accumulator adds its products in increasing d: the reference order.
+// Dense costs: 64x64 output tile per CTA, 256 threads, 4x4 outputs per thread (rows t, t+16, t+32,
+// t+48 so that the 8 lanes of one LDS.128 phase hit 8 consecutive rows = 8 distinct bank groups with
+// the 36-float row stride): 8 LDS.128 feed 64 multiply-adds, which keeps the FP32 pipe - not shared
+// memory - the limit.  32-float slices arrive by cp.async into a double buffer.  Each accumulator
+// adds its products in increasing d: the reference order.
 // ---------------------------------------------------------------------------------------------
-constexpr int kDT = 32;       // tile edge
-constexpr int kDC = 64;       // floats of the embedding dimension staged per step
+constexpr int kDT = 64;       // tile edge
+constexpr int kDC = 32;       // floats of the embedding dimension staged per step
 constexpr int kDS = kDC + 4;  // padded row stride
 
 template <bool EXACT>
@@ -33,41 +35,69 @@ __device__ __forceinline__ void mac4(float &acc, const float4 &a, const float4 &
 template <bool EXACT>
 __global__ void __launch_bounds__(256) k_dense_costs(const SvxDenseJob *jobs, int dim)
 {
-    __shared__ __align__(16) float xs[kDT * kDS];
-    __shared__ __align__(16) float ys[kDT * kDS];
+    __shared__ __align__(16) float xs[2][kDT * kDS];
+    __shared__ __align__(16) float ys[2][kDT * kDS];
     const SvxDenseJob job = jobs[blockIdx.z];
     const int x0 = blockIdx.y * kDT, y0 = blockIdx.x * kDT;
     if (x0 >= job.s0 || y0 >= job.s1) return;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // y rows tx, tx+16; x rows ty, ty+16
-    float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    for (int d0 = 0; d0 < dim; d0 += kDC) {
-        __syncthreads();
-        for (int f = threadIdx.x; f < kDT * (kDC / 4); f += 256) {
-            const int r = f / (kDC / 4), c4 = f % (kDC / 4);
-            float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
-            if (x0 + r < job.s0) vx = ldg_f4(job.v0 + (size_t)(x0 + r) * dim + d0 + 4 * c4);
-            if (y0 + r < job.s1) vy = ldg_f4(job.v1 + (size_t)(y0 + r) * dim + d0 + 4 * c4);
-            *reinterpret_cast<float4 *>(xs + r * kDS + 4 * c4) = vx;
-            *reinterpret_cast<float4 *>(ys + r * kDS + 4 * c4) = vy;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;       // y rows tx + 16 j; x rows ty + 16 i
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // this thread stages 2 pieces (row r, 16-byte piece c4) of each operand per slice
+    auto issue = [&](int sl) {
+        const int d0 = sl * kDC;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int f = tid + it * 256;
+            const int r = f >> 3, c4 = f & 7;
+            const bool okx = x0 + r < job.s0, oky = y0 + r < job.s1;
+            const float *gx = okx ? job.v0 + (size_t)(x0 + r) * dim + d0 + 4 * c4 : job.v0;
+            const float *gy = oky ? job.v1 + (size_t)(y0 + r) * dim + d0 + 4 * c4 : job.v1;
+            const unsigned dx = (unsigned)__cvta_generic_to_shared(&xs[sl & 1][r * kDS + 4 * c4]);
+            const unsigned dy = (unsigned)__cvta_generic_to_shared(&ys[sl & 1][r * kDS + 4 * c4]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dx), "l"(gx), "r"(okx ? 16 : 0));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dy), "l"(gy), "r"(oky ? 16 : 0));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    const int slices = dim / kDC;
+    issue(0);
+    for (int sl = 0; sl < slices; ++sl) {
+        if (sl + 1 < slices) {
+            issue(sl + 1);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
         }
         __syncthreads();
-#pragma unroll 4
+        const float *bx = xs[sl & 1], *by = ys[sl & 1];
+#pragma unroll 2
         for (int d = 0; d < kDC; d += 4) {
-            const float4 a0 = *reinterpret_cast<const float4 *>(xs + ty * kDS + d);
-            const float4 a1 = *reinterpret_cast<const float4 *>(xs + (ty + 16) * kDS + d);
-            const float4 b0 = *reinterpret_cast<const float4 *>(ys + tx * kDS + d);
-            const float4 b1 = *reinterpret_cast<const float4 *>(ys + (tx + 16) * kDS + d);
-            mac4<EXACT>(acc[0][0], a0, b0); mac4<EXACT>(acc[0][1], a0, b1);
-            mac4<EXACT>(acc[1][0], a1, b0); mac4<EXACT>(acc[1][1], a1, b1);
+            float4 a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = *reinterpret_cast<const float4 *>(bx + (ty + 16 * i) * kDS + d);
+                b[i] = *reinterpret_cast<const float4 *>(by + (tx + 16 * i) * kDS + d);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mac4<EXACT>(acc[i][j], a[i], b[j]);
         }
+        __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
         const int x = x0 + ty + 16 * i;
         if (x >= job.s0) continue;
         const float nx = job.n0[x];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int y = y0 + tx + 16 * j;
             if (y < job.s1) {
                 job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(acc[i][j], nx, job.n1[y]);
