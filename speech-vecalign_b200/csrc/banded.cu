@@ -890,10 +890,17 @@ template <int CX, int CY, bool TRI>
 int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, cudaStream_t st)
 {
     const int lb = (band + 7) & ~7;
-    const int ta = 384 / lb < 16 ? 384 / lb : 16;       // <= 384 threads: up to 170 registers each
-    if (ta < 1) return -1;
-    int threads = ta * lb;
+    // anti-diagonals per tile: as many as 384 threads allow, up to 24 (measured: 24 beats 16 by 7 % at K = 5 -
+    // the 2B-1 halo rows of a tile are amortised over more diagonals), 16 if the staging limits say so
     const int maxk = CX > CY ? CX : CY;
+    int ta = 384 / lb < 24 ? 384 / lb : 24;
+    if (ta < 1) return -1;
+    auto fits = [&](int t) {
+        return (size_t)2 * maxk * (t + 2 * band - 1) * kBS * sizeof(float) <= 110 * 1024 &&      // two CTAs per SM
+               (size_t)maxk * (t + 2 * band - 1) * (kBC / 4) <= (size_t)8 * t * lb;                // kMaxItems per thread
+    };
+    if (!fits(ta) && ta > 16) ta = 16;
+    int threads = ta * lb;
     const size_t smem = (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float);   // two slice buffers
     if (smem > 220 * 1024) return -1;
     if ((size_t)maxk * (ta + 2 * band - 1) * (kBC / 4) > (size_t)8 * threads) return -1;   // kMaxItems per thread
