@@ -669,6 +669,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     // reach back >= 2 diagonals).  HOFF = 1 when called one diagonal ahead (history registers still
     // describe a_t - 1 as "current").  Two independent strict-'<' chains (first / second half of the
     // type list) halve the dependent compare-select latency and keep the first-minimum tie-break.
+    const int s0_l = lane < B ? s0 : 0, s1_l = lane < B ? s1 : 0;
     struct Prep {
         double tbest, ovr_val;     // best type candidate; value forced when `ovr`
         int tcode, ovr_code, d1, bo;
@@ -682,14 +683,20 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
         p.d1 = bo_t - bo_prev;
         const int yy = lane + bo_t, xx = a_t - yy;
         // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the deletions -
-        // reference quirk, dp_core.pyx:382,390); lanes >= B and lattice nodes outside the documents hold
-        // +inf, so predecessors outside the node band never win the strict '<' (no range tests below)
-        const bool cell_ok = lane < B && xx >= 1 && xx <= s0 && yy >= 1 && yy <= s1 && a_t - 2 < A;
+        // reference quirk, dp_core.pyx:382,390; its anti-diagonal a_t - 2 < A always holds for a_t <= A + 1);
+        // lanes >= B and lattice nodes outside the documents hold +inf, so predecessors outside the node band
+        // never win the strict '<' (no range tests below).  s0_l / s1_l are 0 for lanes >= B.
+        const bool cell_ok = (unsigned)(xx - 1) < (unsigned)s0_l && (unsigned)(yy - 1) < (unsigned)s1_l;
+        p.ovr = !cell_ok;
+        p.ovr_val = INFINITY;
+        p.ovr_code = SVX_BP_NONE;
+        // boundary nodes (xx == 0 or yy == 0) only occur while the band touches an edge of the lattice
         const bool by = lane < B && xx == 0 && yy >= 0 && yy <= s1;           // csum = pen * yy, bp (0,1)
         const bool bx = lane < B && !by && yy == 0 && xx >= 0 && xx <= s0;    // csum = pen * xx, bp (1,0)
-        p.ovr = !cell_ok;
-        p.ovr_val = by ? __dmul_rn(pen, (double)yy) : (bx ? __dmul_rn(pen, (double)xx) : (double)INFINITY);
-        p.ovr_code = by ? T : (bx ? T + 1 : SVX_BP_NONE);
+        if (__any_sync(0xffffffffu, by || bx)) {
+            if (by) { p.ovr_val = __dmul_rn(pen, (double)yy); p.ovr_code = T; }
+            else if (bx) { p.ovr_val = __dmul_rn(pen, (double)xx); p.ovr_code = T + 1; }
+        }
         double b0 = INFINITY, b1 = INFINITY;
         int c0 = SVX_BP_NONE, c1 = SVX_BP_NONE;
         int t = 0;
