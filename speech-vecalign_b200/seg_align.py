@@ -15,7 +15,8 @@ length-balanced across GPUs; no collective is needed because every process write
 Additions: ``--skip_existing`` (the reference's slow stages do this, preprocess/segment.py:105-128),
 ``--seed`` (the reference draws from the unseeded global RNG; here pair i draws from
 RandomState(crc32(output name) ^ seed), so results do not depend on batching or sharding),
-``--cost_mode exact|fast|tc``.
+``--cost_mode exact|fast|tc``, ``--max_cost`` (writes step 6.1's filtered files from the same records,
+postprocess/filter_by_cost.py:39-87).
 
     python -m speech_vecalign_b200.seg_align metadata.tsv out --src_lang en --tgt_lang de \\
         --seg_dir segments --concat_dir cat_segs --embed_dir embeds --is_stopes_embed -a 6
@@ -59,6 +60,9 @@ def build_parser():
     p.add_argument("--skip_existing", action="store_true")
     p.add_argument("--host_gather", action="store_true", help="build the overlap tensors on the host (reference path) "
                                                              "instead of uploading the .embed rows and gathering on the GPU")
+    p.add_argument("--max_cost", type=float, default=None,
+                   help="also write the step-6.1 output (postprocess/filter_by_cost.py --max_cost) from the same records")
+    p.add_argument("--filter_dir", default=None, help="where the filtered alignments go (default: <out_dir>_<max_cost>)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--cost_mode", default="exact", choices=["exact", "fast", "tc"])
     p.add_argument("--rank", type=int, default=None, help="shard index (default: RANK env, else 0)")
@@ -127,6 +131,32 @@ def load_pair(item, k, args, on_device=False):
     return out[0], out[1]
 
 
+def filter_by_cost(alignments, scores, max_cost):
+    """Step 6.1 applied to fresh records (reference: postprocess/filter_by_cost.py:39-87, which re-parses the
+    step-5.4 text file): insertions / deletions are dropped, then alignments whose cost exceeds max_cost.
+    The cost compared and written is the one a reader of the "%.6f" file would see."""
+    kept = []
+    for (xs, ys), sc in zip(alignments, scores):
+        cost = float("%.6f" % sc)
+        if len(xs) == 0 or len(ys) == 0 or cost > max_cost:
+            continue
+        kept.append((list(xs), list(ys), cost))
+    return kept
+
+
+def write_filtered(path, kept):
+    """filter_by_cost.py:74-80: '<src ids>:<tgt ids>:<cost>' with Python's float repr; nothing is written when
+    every alignment was filtered out."""
+    if not kept:
+        logger.warning("Empty output. Will not write %s", path)
+        return
+    tmp = Path(str(path) + ".tmp")
+    with open(tmp, "w") as f:
+        for xs, ys, cost in kept:
+            f.write(f"{xs}:{ys}:{cost}\n")
+    os.replace(tmp, path)
+
+
 def pair_seed(item, seed):
     return (zlib.crc32(item["out"].name.encode()) ^ (seed & 0xFFFFFFFF)) & 0xFFFFFFFF
 
@@ -146,6 +176,10 @@ def run(args):
     w = width_over2_for(k, k, args.search_buffer_size)
     out_dir, jobs = resolve_pairs(open(args.metadata, "rt", encoding="utf-8"), args)
     out_dir.mkdir(parents=True, exist_ok=True)
+    filt_dir = None
+    if args.max_cost is not None:
+        filt_dir = Path(args.filter_dir or (str(args.out_dir).rstrip("/") + f"_{args.max_cost}")) / f"{args.src_lang}-{args.tgt_lang}"
+        filt_dir.mkdir(parents=True, exist_ok=True)
     if args.skip_existing:
         jobs = [j for j in jobs if not j["out"].exists()]
     sizes = [(_count_lines(j["src_seg"]), _count_lines(j["tgt_seg"])) for j in jobs]
@@ -172,6 +206,8 @@ def run(args):
             with open(tmp, "w") as f:
                 print_alignments(al, scores=sc, ofile=f)
             os.replace(tmp, item["out"])
+            if args.max_cost is not None:                     # step 6.1 straight from the records
+                write_filtered(filt_dir / item["out"].name, filter_by_cost(al, sc, args.max_cost))
         done += len(batch)
         logger.info("shard %d: %d/%d pairs aligned", rank, done, len(jobs))
     return done

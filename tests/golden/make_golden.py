@@ -61,6 +61,7 @@ def example():
     shutil.copy(f"{EX}/untrans_cat_seg_ids/en-de/{NAME}_en-{NAME}_de.src.txt", f"{dst}/ignore.src.txt")
     shutil.copy(f"{EX}/untrans_cat_seg_ids/en-de/{NAME}_en-{NAME}_de.tgt.txt", f"{dst}/ignore.tgt.txt")
     shutil.copy(f"{EX}/alignments/en-de/{NAME}_en-{NAME}_de.txt", f"{dst}/shipped_alignment_a6.txt")
+    shutil.copy(f"{EX}/align_0.7/en-de/{NAME}_en-{NAME}_de.txt", f"{dst}/shipped_align_0.7.txt")   # step 6.1 output (max_cost 0.7)
     shutil.copy(f"{EX}/{NAME}.gold", f"{dst}/human.gold")          # human alignment (README.md:289-296 known answers)
 
     def load(lang, ign, k):

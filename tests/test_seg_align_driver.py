@@ -67,6 +67,13 @@ def test_driver_reproduces_shipped_alignment(tmp_path):
     ref = [float(ln.rsplit(":", 1)[1]) for ln in open(shipped)]
     assert np.max(np.abs(np.array(scores) - np.array(ref))) <= 0.05      # other RNG state
     assert seg_align.main(argv + ["--skip_existing"]) == 0
+    # step 6.1 from the same records: equals the filter applied to the written step-5.4 file
+    out.unlink()
+    assert seg_align.main(argv + ["--max_cost", "0.7"]) == 1
+    filt = tmp_path / "out_0.7" / "en-de" / out.name
+    kept = seg_align.filter_by_cost(read_alignments(str(out)), [float(ln.rsplit(":", 1)[1]) for ln in open(out)], 0.7)
+    assert filt.read_text().splitlines() == [f"{xs}:{ys}:{c}" for xs, ys, c in kept]
+    assert 120 <= len(kept) <= 156
 
 
 @pytest.mark.gpu
@@ -100,3 +107,18 @@ def test_driver_host_and_device_gather_agree(tmp_path):
     out.unlink()
     assert seg_align.main(argv + ["--host_gather"]) == 1
     assert out.read_text() == dev_txt
+
+
+def test_filter_by_cost_known_answer():
+    """Step 6.1 on the shipped step-5.4 file must give the shipped align_0.7 file, line for line
+    (reference README: filter_by_cost --max_cost 0.7)."""
+    from speech_vecalign_b200 import seg_align
+    from speech_vecalign_b200.vecalign import read_alignments
+    ex = os.path.join(GOLDEN, "example")
+    src = os.path.join(ex, "shipped_alignment_a6.txt")
+    al = read_alignments(src)
+    scores = [float(ln.rsplit(":", 1)[1]) for ln in open(src)]
+    kept = seg_align.filter_by_cost(al, scores, 0.7)
+    want = open(os.path.join(ex, "shipped_align_0.7.txt")).read().splitlines()
+    got = [f"{xs}:{ys}:{c}" for xs, ys, c in kept]
+    assert got == want
