@@ -120,7 +120,10 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
     any_host = any(not c0 or not c1 for (_, c0), (_, c1) in metas)
     nchunks = 1
     if any_host and sync and not debug and P >= 16:
-        nchunks = min(8, P // 4)
+        # ~512 MB of embeddings per chunk (10 ms of PCIe): enough chunks to overlap copy and compute, few
+        # enough that per-chunk planning (RNG replay, descriptors) stays off the critical path
+        total_bytes = sum(4 * (sh0[0] * sh0[1] + sh1[0] * sh1[1]) * sh0[2] for (sh0, _), (sh1, _) in metas)
+        nchunks = max(1, min(8, P // 4, int(total_bytes // (512 << 20))))
     bounds = [P * i // nchunks for i in range(nchunks + 1)]
     cur = torch.cuda.current_stream(dev)
     piped = nchunks > 1
