@@ -113,7 +113,8 @@ SVX_API int svx_sample_norms(const SvxNormJob *jobs_d, const SvxNormJob *jobs_h,
  * ---------------------------------------------------------------------------------------------- */
 typedef struct SvxGatherJob {
     const void *rows;        /* (nrows, dim) fp16 or fp32                                  */
-    const int32_t *table;    /* (k, n) source row of every (overlap, position), -1 = zeros */
+    const int32_t *table;    /* (k, n) source row of every (overlap, position), -1 = zeros;
+                                NULL = identity (rows is already (k, n, dim): widen + NaN scrub) */
     float *out;              /* (k, n, dim) fp32                                           */
     int32_t *nan_rows;       /* (1) or NULL: number of output rows zeroed because of NaNs  */
     int32_t k, n, nrows, is_fp16;

@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(const SvxGatherJob *jobs, i
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t total = (int64_t)job.k * job.n;
     for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < total; r += (int64_t)gridDim.x * 8) {
-        const int src = job.table[r];
+        const int src = job.table ? job.table[r] : (int)r;      // no table: identity (a plain widening copy)
         float *dst = job.out + r * dim;
         const bool have = src >= 0 && src < job.nrows;
         bool bad = false;

@@ -47,9 +47,10 @@ def _side_stream(dev, name):
 
 
 def _to_device(v, dev):
-    """(K, N, D) fp32 on the device.  Returns (tensor, host_array_or_None)."""
+    """(K, N, D) on the device, fp32 or — an extension for embeddings kept in their on-disk dtype — fp16
+    (widened on the device by _widen).  Returns (tensor, host_array_or_None)."""
     if isinstance(v, torch.Tensor):
-        if v.dtype != torch.float32 or v.dim() != 3:
+        if v.dtype not in (torch.float32, torch.float16) or v.dim() != 3:
             raise ValueError("Buffer dtype mismatch, expected 'float' (K, N, D) tensor")
         if v.is_cuda:
             if not v.is_contiguous():
@@ -57,11 +58,36 @@ def _to_device(v, dev):
             return v, None
         return v.contiguous().to(dev, non_blocking=True), None
     v = np.asarray(v)
-    if v.dtype != np.float32 or v.ndim != 3:
+    if v.dtype not in (np.float32, np.float16) or v.ndim != 3:
         # the reference's Cython buffers reject anything else (dp_core.pyx:168-171)
         raise ValueError("Buffer dtype mismatch, expected 'float' with ndim=3")
     t = torch.from_numpy(np.ascontiguousarray(v)).to(dev, non_blocking=True)
     return t, v
+
+
+def _widen(pairs_dev, dev):
+    """fp16 device tensors -> fp32 working tensors (svx_gather_doc_embedding with the identity table: a
+    widening copy that also zeroes rows containing NaNs, as make_doc_embedding does).  One launch for
+    all fp16 tensors of the list; fp32 tensors pass through."""
+    todo = [(i, s) for i, pr in enumerate(pairs_dev) for s in (0, 1) if pr[s].dtype == torch.float16]
+    if not todo:
+        return pairs_dev, None
+    out = [list(pr) for pr in pairs_dev]
+    jobs = np.zeros(len(todo), dtype=capi.GATHER)
+    for j, (i, s) in enumerate(todo):
+        src = pairs_dev[i][s]
+        dst = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        out[i][s] = dst
+        jobs[j]["rows"], jobs[j]["out"] = src.data_ptr(), dst.data_ptr()
+        jobs[j]["k"], jobs[j]["n"], jobs[j]["nrows"], jobs[j]["is_fp16"] = src.shape[0], src.shape[1], src.shape[0] * src.shape[1], 1
+    stage = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).pin_memory()
+    jd = torch.empty(stage.numel() + 16, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    capi.check(capi.lib().svx_upload_pinned(jd.data_ptr(), stage.data_ptr(), stage.numel(), stream), "svx_upload_pinned")
+    capi.check(capi.lib().svx_gather_doc_embedding(jd.data_ptr(), capi.hptr(jobs), len(todo), int(pairs_dev[0][0].shape[2]), stream),
+               "svx_gather_doc_embedding")
+    # the launches above are asynchronous: the caller keeps `stage` (pinned) and `jd` alive until it has synchronised
+    return [tuple(pr) for pr in out], (stage, jd, jobs, pairs_dev)
 
 
 def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
@@ -89,11 +115,11 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
 
     def _meta(v):
         if isinstance(v, torch.Tensor):
-            if v.dtype != torch.float32 or v.dim() != 3:
+            if v.dtype not in (torch.float32, torch.float16) or v.dim() != 3:
                 raise ValueError("Buffer dtype mismatch, expected 'float' (K, N, D) tensor")
             return tuple(v.shape), v.is_cuda
         a = np.asarray(v)
-        if a.dtype != np.float32 or a.ndim != 3:
+        if a.dtype not in (np.float32, np.float16) or a.ndim != 3:
             # the reference's Cython buffers reject anything else (dp_core.pyx:168-171)
             raise ValueError("Buffer dtype mismatch, expected 'float' with ndim=3")
         return tuple(a.shape), False
@@ -140,7 +166,7 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
             landed[c].record(copy_stream)
 
     ngroups = (4 if P >= 8 else 1) if streams is None else int(streams)
-    runs = []
+    runs, keepalive = [], []
     import os as _os, time as _time
     _tr = _os.environ.get("SVX_TRACE")
     _t0 = _time.perf_counter()
@@ -164,6 +190,11 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
         if piped and c < 4:
             st.wait_event(fork)
         with torch.cuda.stream(st):
+            if any(t.dtype == torch.float16 for pr in dv[lo:hi] for t in pr):
+                if piped:
+                    st.wait_event(landed[c])
+                dv[lo:hi], alive = _widen(dv[lo:hi], dev)
+                keepalive.append(alive)
             run = BatchRun([t0.data_ptr() for t0, _ in dv[lo:hi]], [t1.data_ptr() for _, t1 in dv[lo:hi]],
                            [t0.shape[1] for t0, _ in dv[lo:hi]], [t1.shape[1] for _, t1 in dv[lo:hi]],
                            k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
@@ -185,6 +216,7 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
             cur.wait_stream(_side_stream(dev, ("chunk", c)))
     run = runs[0]
     if not sync:
+        run._keepalive = keepalive
         return run
     res = []
     if _tr:

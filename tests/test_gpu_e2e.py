@@ -202,3 +202,26 @@ def test_chunked_host_pipeline_equals_serial_loop(svb, oracle):
     for r, g in zip(refs, gots):
         assert same_alignments(g[0]["final_alignments"], r[0]["final_alignments"])
         assert np.max(np.abs(g[0]["alignment_scores"] - r[0]["alignment_scores"]), initial=0) <= 1e-4
+
+
+def test_fp16_inputs_equal_widened_fp32(svb, oracle):
+    """Embeddings kept in their on-disk dtype: fp16 (K, N, D) inputs are widened on the device and must
+    give exactly what the same values passed as fp32 give — single pair, small batch and the
+    chunk-pipelined host path."""
+    from speech_vecalign_b200 import synth
+    a, k = 5, 4
+    types = oracle.alignment_types(a)
+    args = (types, 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    shapes = [(300 + 13 * i, 280 + 17 * i) for i in range(17)]
+    p16 = [tuple(v.astype(np.float16) for v in synth.synth_pair(n0, n1, k, dim=256, seed=50 + i)) for i, (n0, n1) in enumerate(shapes)]
+    p32 = [(v0.astype(np.float32), v1.astype(np.float32)) for v0, v1 in p16]
+    seeds = list(range(len(shapes)))
+    r16 = svb.vecalign_batch(p16, *args, output="records", seeds=seeds)
+    r32 = svb.vecalign_batch(p32, *args, output="records", seeds=seeds)
+    for x, y in zip(r16, r32):
+        assert np.array_equal(x["recs"], y["recs"]) and x["del_penalty"] == y["del_penalty"]
+    np.random.seed(3)
+    one16 = svb.dp_utils.vecalign(p16[0][0], p16[0][1], *args)
+    np.random.seed(3)
+    ref = oracle.vecalign(p32[0][0].copy(), p32[0][1].copy(), *args, fast_host=True)
+    assert same_alignments(one16[0]["final_alignments"], ref[0]["final_alignments"])
