@@ -506,16 +506,18 @@ __global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R
             const int start = c * kChunk;
             const int end = min(start + kChunk, nodes_a);
             for (int aa = start; aa < end; ++aa) {
-                if (lane < B) {
+                // bands wider than a warp (large search_buffer_size): a lane takes slots lane, lane+32, ...;
+                // the nodes of one diagonal only read older diagonals, so their order does not matter
+                for (int bb = lane; bb < B; bb += 32) {
                     int bp;
                     auto boff = [&](int q) { return bo[q - start + R]; };            // q in (aa-R, aa]
                     auto csum_at = [&](int aq, int bq) { return sm.ring[(size_t)(aq & (R - 1)) * B + bq]; };
-                    auto cost_at = [&](int t) { return cb[(size_t)(aa - start) * tb + (size_t)t * B + lane]; };
-                    const double v = svx_band_node(aa, lane, s0, s1, A, B, T, sxo, syo, pen, boff, csum_at, cost_at, &bp);
+                    auto cost_at = [&](int t) { return cb[(size_t)(aa - start) * tb + (size_t)t * B + bb]; };
+                    const double v = svx_band_node(aa, bb, s0, s1, A, B, T, sxo, syo, pen, boff, csum_at, cost_at, &bp);
                     // ring slot aa & (R-1) held diagonal aa - R, which no type can reach any more
-                    sm.ring[(size_t)(aa & (R - 1)) * B + lane] = v;
-                    job.bp[(size_t)aa * B + lane] = (uint8_t)bp;
-                    job.csum[(size_t)aa * B + lane] = v;
+                    sm.ring[(size_t)(aa & (R - 1)) * B + bb] = v;
+                    job.bp[(size_t)aa * B + bb] = (uint8_t)bp;
+                    job.csum[(size_t)aa * B + bb] = v;
                 }
                 __syncwarp();
             }
@@ -1023,7 +1025,7 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
     bool standard = true;
     for (int j = 0; j < njobs; ++j) {
         const SvxBandJob &jb = jobs_h[j];
-        SVX_REQUIRE(jb.band >= 2 && jb.band <= 32, SVX_ERR_UNSUPPORTED, "svx_banded_dp: band %d must be in [2,32]", jb.band);
+        SVX_REQUIRE(jb.band >= 2 && jb.band <= 256, SVX_ERR_UNSUPPORTED, "svx_banded_dp: band %d must be in [2,256]", jb.band);
         SVX_REQUIRE(jb.ntypes >= 0 && jb.ntypes <= SVX_MAX_TYPES - 2, SVX_ERR_ARG, "svx_banded_dp: too many types");
         SVX_REQUIRE(jb.a_len >= 1, SVX_ERR_ARG, "svx_banded_dp: empty search path");
         for (int t = 0; t < jb.ntypes; ++t) if (jb.xo[t] + jb.yo[t] > amax) amax = jb.xo[t] + jb.yo[t];

@@ -225,3 +225,26 @@ def test_fp16_inputs_equal_widened_fp32(svb, oracle):
     np.random.seed(3)
     ref = oracle.vecalign(p32[0][0].copy(), p32[0][1].copy(), *args, fast_host=True)
     assert same_alignments(one16[0]["final_alignments"], ref[0]["final_alignments"])
+
+
+@pytest.mark.parametrize("sbs,a", [(15, 4), (30, 3)])
+def test_wide_search_buffer(svb, oracle, sbs, a):
+    """search_buffer_size large enough that the band (2 * width_over2) exceeds a warp: the generic
+    wavefront kernel takes several band slots per lane."""
+    ref, got = _run_both(svb, oracle, 340, 330, a, seed=60 + sbs, search_buffer_size=sbs, dim=256)
+    _compare(ref, got)
+
+
+def test_many_to_one_types(svb, oracle):
+    """vecalign.py:165-171 make_many_to_one_alignment_types: a non-standard type list (generic kernels)."""
+    from speech_vecalign_b200 import synth
+    types = svb.make_many_to_one_alignment_types(4)
+    assert types == [(1, 1), (2, 1), (3, 1), (4, 1)]
+    v0, v1 = synth.synth_pair(420, 380, 4, dim=256, seed=77)
+    v1 = v1[:1].copy()                                   # the target side only provides overlap 0
+    w = math.ceil(4 / 2) + 5
+    np.random.seed(4)
+    ref = oracle.vecalign(v0.copy(), v1.copy(), types, 0.2, w, 300, 20000, 100, fast_host=True)
+    np.random.seed(4)
+    got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), types, 0.2, w, 300, 20000, 100, debug=True)
+    _compare(ref, got)
