@@ -58,3 +58,27 @@ def test_align_entry_point_on_shipped_example(svb, tmp_path, a):
         assert same_alignments(got, read_alignments(shipped))
         file_scores = [float(ln.rsplit(":", 1)[1]) for ln in open(shipped)]
         assert np.max(np.abs(np.array(scores) - np.array(file_scores))) <= 0.05
+
+
+def test_align_gold_scoring_and_debug_stack(svb, tmp_path, capsys):
+    """align(gold_alignment=..., debug_save_stack=...) (vecalign.py:287-293): the README's P/R/F table is
+    printed for the shipped example and the pickled stack carries the reference's keys."""
+    import pickle
+    ex = os.path.join(GOLDEN, "example")
+    stack_path = tmp_path / "stack.pkl"
+    np.random.seed(0)
+    svb.align(src=f"{ex}/en.segments.txt", tgt=f"{ex}/de.segments.txt",
+              src_embed=[f"{ex}/en.cat_segs.txt", f"{ex}/en.embed"], src_stopes=True, tgt_stopes=True,
+              tgt_embed=[f"{ex}/de.cat_segs.txt", f"{ex}/de.embed"], alignment_max_size=6, many_to_one=None,
+              search_buffer_size=5, del_percentile_frac=0.2, max_size_full_dp=300, costs_sample_size=20000,
+              num_samps_for_norm=100, overlap_segments=True, print_aligned_text=False,
+              src_ignore_indices=f"{ex}/ignore.src.txt", tgt_ignore_indices=f"{ex}/ignore.tgt.txt",
+              debug_save_stack=str(stack_path), gold_alignment=f"{ex}/human.gold")
+    err = capsys.readouterr().err
+    assert "0.558" in err and "0.942" in err and "0.632" in err and "0.993" in err      # README.md:289-296
+    stack = pickle.load(open(stack_path, "rb"))
+    for key in ("v0", "v1", "size0", "size1", "alignment_types", "n0", "n1", "del_penalty", "searchpath", "a_b_costs",
+                "b_offset", "a_b_csum", "a_b_xp", "a_b_yp", "new_b_offset", "alignment_scores", "final_alignments",
+                "costs_1to1", "x_y_tb", "alignments"):
+        assert key in stack[0], key
+    assert stack[0]["a_b_costs"].shape == (15, 237 + 217 + 1, 16)
