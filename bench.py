@@ -164,7 +164,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": ref.nproc, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -468,21 +468,55 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "wall_s_timed_loop": t_wall,
         "roofline": roofline, "serial_chain_ms_per_step": serial_ms, "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """Everything libraries print on fd 1 while the benchmark runs (NCCL's version banner, warnings of forked
+    workers) goes to stderr; stdout carries exactly one line: the JSON record."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+OUT = None
+
+
+def emit(line):
+    if OUT is not None:
+        OUT.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global OUT
     args = parse_args()
     if args.gpus > 1 and "RANK" not in os.environ and args.impl == "ours":
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with StdoutToStderr() as OUT:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
