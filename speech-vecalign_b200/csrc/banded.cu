@@ -210,7 +210,7 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
 constexpr int kBlkTA = 30;      // 16 block-diagonals per tile (kBlkTA / 2 + 1): a quarter-warp = 8 consecutive block-diagonals
 
 template <int K, bool EXACT>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(160, 3)
 k_banded_costs_blk(const SvxBandJob *jobs, int dim)
 {
     constexpr int T = K * (K + 1) / 2;
@@ -232,7 +232,7 @@ k_banded_costs_blk(const SvxBandJob *jobs, int dim)
     const int xlo = ((d_first - (bf + B - 1)) >> 1) * 2, xhi = ((d_last - bl) >> 1) * 2 + 1;
     const int NX = xhi - xlo + 1, NY = yhi - ylo + 1, HX = NX >> 1, HY = NY >> 1;
     const int nrows = K * (NX + NY);
-    const int rows_cap = K * (kBlkTA + 2 * B + 6);
+    const int rows_cap = K * (kBlkTA + 2 * B + 4);
     const int buf_floats = rows_cap * kBS;
     int *srcoff = reinterpret_cast<int *>(tile + 2 * buf_floats);        // float offset from v0 / v1, -1 = zero row
 
@@ -378,8 +378,8 @@ int launch_costs_blk(const SvxBandJob *jobs_d, int nj, int max_alen, int band, i
 {
     const int nb = band / 2 + 2, ne = kBlkTA / 2 + 1;
     const int threads = ((nb * ne + 31) / 32) * 32;
-    if (threads > 192) return -1;
-    const int rows_cap = K * (kBlkTA + 2 * band + 6);
+    if (threads > 160) return -1;
+    const int rows_cap = K * (kBlkTA + 2 * band + 4);
     const size_t smem = (size_t)2 * rows_cap * kBS * sizeof(float) + (size_t)rows_cap * sizeof(int);
     if (smem > 200 * 1024) return -1;
     dim3 grid((max_alen + kBlkTA - 1) / kBlkTA, nj);
