@@ -904,23 +904,30 @@ int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int d
     const int maxk = CX > CY ? CX : CY;
     int ta = 384 / lb < 24 ? 384 / lb : 24;
     if (ta < 1) return -1;
+    // threads = one per band cell, plus staging-only threads when a narrow band leaves too few of them
+    // to move the tile's rows in kMaxItems (8) pieces each
+    auto threads_for = [&](int t) {
+        const size_t items = (size_t)maxk * (t + 2 * band - 1) * (kBC / 4);
+        const int need = (int)(((items + 7) / 8 + 31) & ~(size_t)31);
+        return need > t * lb ? need : t * lb;
+    };
     auto fits = [&](int t) {
         return (size_t)2 * maxk * (t + 2 * band - 1) * kBS * sizeof(float) <= 110 * 1024 &&      // two CTAs per SM
-               (size_t)maxk * (t + 2 * band - 1) * (kBC / 4) <= (size_t)8 * t * lb;                // kMaxItems per thread
+               threads_for(t) <= 384;
     };
     if (!fits(ta) && ta > 16) ta = 16;
-    int threads = ta * lb;
+    const int threads = threads_for(ta);
+    if (threads > 384) return -1;
     const size_t smem = (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float);   // two slice buffers
     if (smem > 220 * 1024) return -1;
-    if ((size_t)maxk * (ta + 2 * band - 1) * (kBC / 4) > (size_t)8 * threads) return -1;   // kMaxItems per thread
     dim3 grid((max_alen + ta - 1) / ta, nj);
     if (mode == SVX_COST_EXACT) {
         auto kern = k_banded_costs<CX, CY, TRI, true>;
-        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 36 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta, lb);
     } else {
         auto kern = k_banded_costs<CX, CY, TRI, false>;
-        if (smem > 48 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > 36 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(jobs_d, dim, ta, lb);
     }
     SVX_LAUNCH_CHECK();
@@ -1002,6 +1009,7 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
     const int tb = T * bmax;
     int chunk = (int)((64 * 1024) / ((size_t)2 * tb * sizeof(float)));
     chunk = chunk > kMaxChunk ? kMaxChunk : (chunk < 4 ? 4 : chunk);
+    chunk &= ~1;       // even: chunk * tb floats is then a multiple of 4 (B is even), the 16-byte cp.async staging relies on it
     const size_t dp_bytes = (size_t)2 * (chunk * tb + 32) * sizeof(float) + (size_t)2 * chunk * sizeof(int);
     // walk window: whole job when it fits in ~96 KB, otherwise 96 KB windows
     const int per_diag = bmax + (int)sizeof(int);
