@@ -70,3 +70,66 @@ def test_random_configuration(svb, oracle, case):
             assert np.max(np.abs(g["alignment_scores"] - r["alignment_scores"]), initial=0) <= 1e-4, d
         if "costs_1to1" in r:
             assert same_alignments(g["alignments"], r["alignments"]), d
+
+
+def _draw_wide(n, seed):
+    """alignment_max_size 9..13: K = 8..12 overlaps -> the K > 9 cases leave the templated type-triangle
+    kernels for the generic (type-table) cost and DP kernels."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        n0 = int(rng.integers(20, 260))
+        out.append(dict(n0=n0, n1=max(1, int(n0 * rng.uniform(0.7, 1.3))), a=int(rng.integers(9, 14)),
+                        sbs=int(rng.integers(1, 6)), full=int(rng.choice([40, 90])), seed=3000 + i))
+    return out
+
+
+@pytest.mark.parametrize("case", _draw_wide(10, 7), ids=lambda c: f"{c['n0']}x{c['n1']}-a{c['a']}-b{c['sbs']}-f{c['full']}")
+def test_random_wide_type_sets(svb, oracle, case):
+    from speech_vecalign_b200 import synth
+    a, k = case["a"], case["a"] - 1
+    v0, v1 = synth.synth_pair(case["n0"], case["n1"], k, dim=128, seed=case["seed"])
+    args = (oracle.alignment_types(a), 0.2, math.ceil(k / 2) + case["sbs"], case["full"], 2000, 50)
+    np.random.seed(case["seed"])
+    ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+    np.random.seed(case["seed"])
+    got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args, debug=True)
+    for d in sorted(ref, reverse=True):
+        r, g = ref[d], got[d]
+        if abs(g["del_penalty"] - r["del_penalty"]) > 1e-6:          # knob tie (module docstring)
+            assert abs(g["del_penalty"] - r["del_penalty"]) <= float(np.max(r["sample_scores"])) / 1000 * (1 + 1e-6)
+            _bin_events.append(case)
+            assert len(_bin_events) <= 2, _bin_events
+            return
+        key = "final_alignments" if d == 0 and "final_alignments" in r else "alignments"
+        assert same_alignments(g[key], r[key]), d
+        if "a_b_costs" in r:
+            fin = np.isfinite(r["a_b_costs"])
+            assert np.array_equal(np.isfinite(g["a_b_costs"]), fin), d
+            assert np.max(np.abs(g["a_b_costs"][fin] - r["a_b_costs"][fin]), initial=0) <= 2e-4, d
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_ragged_batch(svb, oracle, seed):
+    """One vecalign_batch call over 20 pairs of unrelated sizes (1 .. 900 segments, some single-level, some
+    four levels deep): per-pair records equal the oracle run with the same per-pair seed."""
+    from speech_vecalign_b200 import synth
+    from speech_vecalign_b200.engine import records_to_alignments
+    rng = np.random.default_rng(seed)
+    a = int(rng.integers(2, 8))
+    k = a - 1
+    shapes = [(int(n), max(1, int(n * rng.uniform(0.5, 1.6)))) for n in rng.integers(1, 900, size=20)]
+    args = (oracle.alignment_types(a), 0.2, math.ceil(k / 2) + int(rng.integers(2, 7)), int(rng.choice([50, 120, 300])), 3000, 30)
+    pairs = [synth.synth_pair(n0, n1, k, dim=128, seed=seed * 100 + i) for i, (n0, n1) in enumerate(shapes)]
+    seeds = [seed * 1000 + i for i in range(len(pairs))]
+    res = svb.vecalign_batch([(v0.copy(), v1.copy()) for v0, v1 in pairs], *args, output="records", seeds=seeds)
+    ties = 0
+    for (v0, v1), s, r in zip(pairs, seeds, res):
+        np.random.seed(s)
+        ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+        al, sc = records_to_alignments(r["recs"])
+        if not same_alignments(al, ref[0]["final_alignments"]):
+            ties += 1                     # only a knob tie (module docstring) may change an alignment
+            continue
+        assert np.max(np.abs(np.asarray(sc) - np.asarray(ref[0]["alignment_scores"])), initial=0) <= 1e-4
+    assert ties <= 1, ties
