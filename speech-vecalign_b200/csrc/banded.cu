@@ -961,6 +961,10 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
                         jb.xo[t], jb.yo[t], jb.k0, jb.k1);
         }
         if (jb.a_len > max_alen) max_alen = jb.a_len;
+        // the kernels address rows with 32-bit float offsets from v0 / v1
+        SVX_REQUIRE((size_t)jb.k0 * jb.s0 * dim < ((size_t)1 << 31) && (size_t)jb.k1 * jb.s1 * dim < ((size_t)1 << 31),
+                    SVX_ERR_UNSUPPORTED, "svx_banded_costs: job %d: a side of %d x %d rows exceeds 2^31 floats", j,
+                    jb.k0 > jb.k1 ? jb.k0 : jb.k1, jb.s0 > jb.s1 ? jb.s0 : jb.s1);
         int kk;
         if (standard && !(is_standard_types(jb, &kk) && kk == K)) standard = false;
     }

@@ -7,9 +7,13 @@ One documented exception (parity): the reference's DeletionKnob quant
 points to histogram bins whose float32 edges depend on max(sampled scores).  When a cumulative count lands
 exactly on a percentile point (e.g. a full n0*n1 grid whose size is a multiple of 14), the side it falls on is
 decided by ulp-level noise of the scores - which differ between the reference's BLAS norms and any other
-summation order.  Such a level shows a del_penalty difference of a fraction of ONE bin (<= max/1000); it is
-accepted here, the levels after it are not compared, and at most 2 of the drawn cases may hit it."""
+summation order.  Such a level shows a del_penalty difference of one bin (max/1000; more when the neighbouring bins
+are empty, as on coarse levels with few samples).  What IS checked on every level: the sampled scores agree
+with the oracle's to 3 ulp, and the CUDA knob equals the oracle's knob evaluated on the CUDA path's own scores
+bit for bit.  A tie level ends the comparison of that case; at most 1 in 15 drawn cases may hit one (a soak run
+of 500 cases hit 3)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -33,9 +37,29 @@ def _draw_cases(n, seed):
 
 
 _bin_events = []
+# soak runs: SVX_FUZZ_CASES=400 SVX_FUZZ_SEED=99 python -m pytest tests/test_gpu_random_configs.py
+_N_CASES = int(os.environ.get("SVX_FUZZ_CASES", "36"))
+_SEED = int(os.environ.get("SVX_FUZZ_SEED", "2024"))
+_MAX_TIES = max(2, _N_CASES // 15)
 
 
-@pytest.mark.parametrize("case", _draw_cases(36, 2024), ids=lambda c: f"{c['n0']}x{c['n1']}-a{c['a']}-b{c['sbs']}-f{c['full']}")
+def _knob_tie(oracle, r, g, case):
+    """The level's sampled scores agree to 3 ulp and the CUDA knob equals the oracle's knob evaluated on the
+    CUDA path's OWN scores bit for bit; returns True when the penalty nevertheless differs from the oracle's
+    (a tie decided by ulp noise, module docstring) - the caller stops comparing that case."""
+    rs, gs = np.asarray(r["sample_scores"], np.float32), np.asarray(g["sample_scores"], np.float32)
+    assert rs.shape == gs.shape and np.max(np.abs(rs - gs), initial=0) <= 4e-7
+    knob = oracle.PercentileKnob(gs, 0, max(gs)) if case.get("css", 1) > 0 and gs.size else None
+    if knob is not None:
+        assert float(g["del_penalty"]) == float(knob.percentile_frac_to_del_penalty(case.get("frac", 0.2)))
+    if abs(g["del_penalty"] - r["del_penalty"]) <= 1e-6 * max(1.0, abs(r["del_penalty"])):
+        return False
+    _bin_events.append(case)
+    assert len(_bin_events) <= _MAX_TIES, _bin_events
+    return True
+
+
+@pytest.mark.parametrize("case", _draw_cases(_N_CASES, _SEED), ids=lambda c: f"{c['n0']}x{c['n1']}-a{c['a']}-b{c['sbs']}-f{c['full']}")
 def test_random_configuration(svb, oracle, case):
     from speech_vecalign_b200 import synth
     a, k = case["a"], case["a"] - 1
@@ -53,12 +77,7 @@ def test_random_configuration(svb, oracle, case):
     for d in sorted(ref, reverse=True):
         r, g = ref[d], got[d]
         assert np.array_equal(g["v0"], r["v0"]) and np.array_equal(g["v1"], r["v1"]), d
-        diff = abs(g["del_penalty"] - r["del_penalty"])
-        if diff > 1e-6 * max(1.0, abs(r["del_penalty"])):
-            one_bin = float(np.max(r["sample_scores"])) / 1000.0
-            assert diff <= one_bin * (1 + 1e-6), (d, diff, one_bin)
-            _bin_events.append(case)
-            assert len(_bin_events) <= 2, _bin_events
+        if _knob_tie(oracle, r, g, case):
             return
         if "searchpath" in r:
             assert g["searchpath"] == [tuple(p) for p in r["searchpath"]], d
@@ -96,10 +115,7 @@ def test_random_wide_type_sets(svb, oracle, case):
     got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args, debug=True)
     for d in sorted(ref, reverse=True):
         r, g = ref[d], got[d]
-        if abs(g["del_penalty"] - r["del_penalty"]) > 1e-6:          # knob tie (module docstring)
-            assert abs(g["del_penalty"] - r["del_penalty"]) <= float(np.max(r["sample_scores"])) / 1000 * (1 + 1e-6)
-            _bin_events.append(case)
-            assert len(_bin_events) <= 2, _bin_events
+        if _knob_tie(oracle, r, g, case):
             return
         key = "final_alignments" if d == 0 and "final_alignments" in r else "alignments"
         assert same_alignments(g[key], r[key]), d
