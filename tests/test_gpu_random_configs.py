@@ -149,3 +149,27 @@ def test_random_ragged_batch(svb, oracle, seed):
             continue
         assert np.max(np.abs(np.asarray(sc) - np.asarray(ref[0]["alignment_scores"])), initial=0) <= 1e-4
     assert ties <= 1, ties
+
+
+@pytest.mark.parametrize("mode,bar", [("fast", 2e-6), ("tc", 1e-5)])
+def test_random_configurations_other_cost_modes(svb, oracle, mode, bar):
+    """cost_mode 'fast' (FMA) and 'tc' (tcgen05 3xTF32 coarsest level) over 30 drawn configurations: every
+    launch succeeds whatever the shape, the coarsest level's costs stay within the mode's stated tolerance,
+    and the final alignment equals the exact path's in (nearly) every case - the modes may only move exact
+    near-ties."""
+    from speech_vecalign_b200 import synth
+    differ = 0
+    cases = _draw_cases(30, 555)
+    for case in cases:
+        a, k = case["a"], case["a"] - 1
+        v0, v1 = synth.synth_pair(case["n0"], case["n1"], k, dim=case["dim"], seed=case["seed"])
+        args = (oracle.alignment_types(a), case["frac"], math.ceil(k / 2) + case["sbs"], case["full"], case["css"], case["nsn"])
+        np.random.seed(case["seed"])
+        ref = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args, debug=True)
+        np.random.seed(case["seed"])
+        got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args, cost_mode=mode, debug=True)
+        top = max(ref)
+        err = np.max(np.abs(got[top]["costs_1to1"].astype(np.float64) - ref[top]["costs_1to1"]), initial=0)
+        assert err <= bar, (case, err)
+        differ += not same_alignments(got[0]["final_alignments"], ref[0]["final_alignments"])
+    assert differ <= 2, differ
