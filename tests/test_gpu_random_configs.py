@@ -173,3 +173,40 @@ def test_random_configurations_other_cost_modes(svb, oracle, mode, bar):
         assert err <= bar, (case, err)
         differ += not same_alignments(got[0]["final_alignments"], ref[0]["final_alignments"])
     assert differ <= 2, differ
+
+
+def _draw_skewed(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        small, big = int(rng.integers(1, 60)), int(rng.integers(1, 900))
+        n0, n1 = (small, big) if i % 2 else (big, small)
+        out.append(dict(n0=n0, n1=n1, a=int(rng.integers(2, 8)), sbs=int(rng.integers(1, 8)),
+                        full=int(rng.choice([20, 64, 300])), seed=5000 + i))
+    return out
+
+
+@pytest.mark.parametrize("case", _draw_skewed(24, 21), ids=lambda c: f"{c['n0']}x{c['n1']}-a{c['a']}-b{c['sbs']}-f{c['full']}")
+def test_random_skewed_documents(svb, oracle, case):
+    """Very unequal document lengths (1..60 against 1..900 segments): the coarse levels shrink one side to a
+    handful of rows (or to none), the band leaves the lattice on one side.  Same alignments as the oracle -
+    or the same failure when the reference's traceback leaves its band ('traceback bug', dp_utils.py:107)."""
+    from speech_vecalign_b200 import synth
+    a, k = case["a"], case["a"] - 1
+    v0, v1 = synth.synth_pair(case["n0"], case["n1"], k, dim=128, seed=case["seed"])
+    args = (oracle.alignment_types(a), 0.2, math.ceil(k / 2) + case["sbs"], case["full"], 3000, 40)
+    np.random.seed(case["seed"])
+    try:
+        ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+    except Exception as exc:                 # noqa: BLE001 - whatever the reference raises, we must raise too
+        np.random.seed(case["seed"])
+        with pytest.raises(Exception):
+            svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args)
+        return
+    np.random.seed(case["seed"])
+    got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args, debug=True)
+    for d in sorted(ref, reverse=True):
+        if _knob_tie(oracle, ref[d], got[d], dict(case, frac=0.2)):
+            return
+        key = "final_alignments" if "final_alignments" in ref[d] else "alignments"
+        assert same_alignments(got[d][key], ref[d][key]), d
