@@ -253,8 +253,8 @@ __global__ void __launch_bounds__(512) k_sort_samples(const SvxScoreJob *jobs)
 // A warp scores 32 samples.  Each lane must consume its own two rows in increasing d (the
 // reference's summation order), but 32 lanes streaming 32 different rows would cost one L1 tag
 // look-up per lane and 16 bytes: instead the warp fetches every 128-byte row piece with 8 lanes
-// (coalesced LDG.128, 4 rows per instruction), parks the 32 x 32-float block in shared memory
-// (row stride 36 floats: conflict-free for the store and for the per-lane LDS.128 read-back) and each
+// (coalesced 16-byte cp.async, 4 rows per instruction) into a 32 x 32-float block of shared memory
+// (row stride 36 floats: conflict-free for the copy and for the per-lane LDS.128 read-back) and each
 // lane then reads its own row back.
 constexpr int kScWarps = 4;
 constexpr int kScStride = 36;
@@ -262,7 +262,7 @@ constexpr int kScStride = 36;
 template <bool EXACT>
 __global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob *jobs, int dim)
 {
-    __shared__ __align__(16) float sy[kScWarps][32 * kScStride];
+    __shared__ __align__(16) float sy[kScWarps][2][32 * kScStride];
     const SvxScoreJob job = jobs[blockIdx.y];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int base = (blockIdx.x * kScWarps + warp) * 32;
@@ -280,29 +280,43 @@ __global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob
     if (job.dots) {
         if (valid) dot = job.dots[(size_t)xi * job.nf + yi];
     } else {
-        // y rows: fetched by this lane in load step g: sample 4g + lane/8, 16-byte piece lane%8.
+        // y rows: moved global -> shared by cp.async (no register staging, no STS wavefronts - the LSU data
+        // pipe is what bounds this kernel), this lane copying in step g the 16-byte piece lane%8 of sample
+        // 4g + lane/8; double-buffered, so block d0 + 32 is in flight while block d0 is consumed.
         // x rows: the samples are sorted by x, so the warp's 32 samples share a handful of x rows; each
         // lane reads its own x row directly (lanes with the same row hit the same 16 bytes: one L1
         // tag per distinct row), no staging.
         const int sub = lane >> 3, piece = 4 * (lane & 7);
-        int yr[8];
+        const float *ysrc[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) yr[g] = __shfl_sync(0xffffffffu, yi, 4 * g + sub);
-        float *my = sy[warp];
+        for (int g = 0; g < 8; ++g) ysrc[g] = job.f + (size_t)__shfl_sync(0xffffffffu, yi, 4 * g + sub) * dim + piece;
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(&sy[warp][0][0]) + (unsigned)((sub * kScStride + piece) * sizeof(float));
+        auto issue = [&](int d0, int buf) {
+            const unsigned dst = sbase + (unsigned)(buf * 32 * kScStride * sizeof(float));
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + (unsigned)(4 * g * kScStride * sizeof(float))),
+                             "l"(ysrc[g] + d0));
+            asm volatile("cp.async.commit_group;\n" ::);
+        };
         const float *xrow = job.e + (size_t)xi * dim;
-        for (int d0 = 0; d0 < dim; d0 += 32) {
-            float4 vy[8], vx[8];
-#pragma unroll
-            for (int g = 0; g < 8; ++g) vy[g] = ldg_f4(job.f + (size_t)yr[g] * dim + d0 + piece);
+        issue(0, 0);
+        for (int d0 = 0, buf = 0; d0 < dim; d0 += 32, buf ^= 1) {
+            float4 vx[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) vx[q] = ldg_f4(xrow + d0 + 4 * q);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) *reinterpret_cast<float4 *>(my + (4 * g + sub) * kScStride + piece) = vy[g];
+            if (d0 + 32 < dim) {
+                issue(d0 + 32, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;\n" ::);
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::);
+            }
             __syncwarp();
+            const float *my = &sy[warp][buf][lane * kScStride];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 a = vx[q];
-                const float4 b = *reinterpret_cast<const float4 *>(my + lane * kScStride + 4 * q);
+                const float4 b = *reinterpret_cast<const float4 *>(my + 4 * q);
                 if (EXACT) {
                     dot = __fadd_rn(dot, __fmul_rn(a.x, b.x)); dot = __fadd_rn(dot, __fmul_rn(a.y, b.y));
                     dot = __fadd_rn(dot, __fmul_rn(a.z, b.z)); dot = __fadd_rn(dot, __fmul_rn(a.w, b.w));
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(kScWarps * 32) k_score_pairs(const SvxScoreJob
                     dot = fmaf(a.z, b.z, dot); dot = fmaf(a.w, b.w, dot);
                 }
             }
-            __syncwarp();
+            __syncwarp();           // every lane is done with `buf` before the next iteration refills it
         }
     }
     if (valid) job.scores[i] = svx_pair_score(dot, job.norm_e[xi], job.norm_f[yi]);
