@@ -391,7 +391,11 @@ def run_ours(args):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks else \
         (6650.0, "fallback (B200_PROFILING.md)")
     alg = run.algorithmic_bytes()
-    dom = max(ktimes, key=ktimes.get)
+    # dominant launcher = the longest one; launchers within 5 % of it count as tied, and among those the
+    # HBM-bound one is reported (the roofline is stated in GB/s; every launcher is listed under "kernels")
+    top_ms = max(ktimes.values())
+    tied = [k for k, v in ktimes.items() if v >= 0.95 * top_ms]
+    dom = "svx_level_prologue" if "svx_level_prologue" in tied else max(tied, key=ktimes.get)
     dom_ms = ktimes[dom]
     achieved = alg.get(dom, 0) / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic = None
