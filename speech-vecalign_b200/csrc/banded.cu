@@ -4,7 +4,9 @@
 //   svx_banded_dp    (dp_core.pyx:269-404 sparse_dp; dp_utils.py:89-143 sparse_traceback +
 //                     process_scores; dp_utils.py:177-275 path glue)
 #include <stdlib.h>
+#include <stdio.h>
 #include <type_traits>
+#include <utility>
 #include "svx_common.cuh"
 #include "svx_dp.h"
 
@@ -495,6 +497,9 @@ __global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R
     };
 
     const int nchunks = (nodes_a + kChunk - 1) / kChunk;
+#ifdef SVX_DP_TIMING
+    long long tm0 = clock64(), tm1 = 0, tm2 = 0;
+#endif
     stage(0, tid, blockDim.x);
     __syncthreads();
     for (int c = 0; c < nchunks; ++c) {
@@ -554,14 +559,18 @@ __global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R
 // Banded DP, standard type set (make_alignment_types(K+1), vecalign.py:154-162; K = 1 for the
 // coarser levels).  One CTA of 4 warps per job.
 //
-//   phase 1  warp 0 runs the recurrence, lane = band slot.  The last K+1 diagonals of fp64
-//            cumulative costs live in REGISTERS; the predecessor of a candidate (dx,dy) on
-//            diagonal aa-(dx+dy) sits in lane  b + (boff(aa) - boff(aa-dx-dy)) - dy,  a shift that
-//            is uniform over the warp, so each candidate is one 64-bit warp shuffle + one DADD
-//            + one compare, with the type loop fully unrolled in the reference's priority order
-//            (types, then (0,1), then (1,0); strict '<' keeps the first minimum).  Warps 1-3
-//            stream the cost diagonals (contiguous T*B floats each) and band offsets into a
-//            shared-memory double buffer.  uint8 backpointers and fp64 csum go to HBM.
+//   phase 1  warp 0 runs the recurrence, lane = band slot.  The fp64 cumulative costs of the last
+//            K+1 diagonals live in a shared-memory ring whose rows are compile-time constants (the
+//            diagonal loop is unrolled K+1 times); the predecessor of a candidate (dx,dy) on diagonal
+//            aa-(dx+dy) sits at lane  b + (boff(aa) - boff(aa-dx-dy)) - dy,  a shift that is uniform over
+//            the warp and precomputed per diagonal, so each candidate is one add, two LDS.64, one DADD
+//            and one compare-select, in the reference's priority order (types, then (0,1), then (1,0);
+//            strict '<' keeps the first minimum).  The two deletion candidates - the serial chain -
+//            stay in registers (64-bit shuffles).  Warps 1-3 prepare everything that does not depend
+//            on the chain, one chunk ahead: cost diagonals widened to fp64, band-offset differences,
+//            forced values of boundary / outside nodes; and they flush the finished chunk's uint8
+//            backpointers and fp64 csum to HBM.  (Measured: 705 -> 530 cycles per diagonal at K = 4;
+//            the bare DADD -> SHFL -> compare chain is 68.)
 //   phase 2  thread 0 walks the backpointers from (s0,s1) through a shared-memory window of
 //            backpointers + band offsets (reloaded, coalesced, when the walk leaves it) and
 //            writes the integer fields of the alignment records.
@@ -569,6 +578,12 @@ __global__ void __launch_bounds__(128) k_banded_dp(const SvxBandJob *jobs, int R
 //            path of the next finer level, one alignment (+ the deletion run that follows it)
 //            per thread; long slanted segments are expanded by the whole CTA.
 // ---------------------------------------------------------------------------------------------
+template <class F, int... Us>
+__device__ __forceinline__ void svx_static_for(F &f, std::integer_sequence<int, Us...>)
+{
+    (f(std::integral_constant<int, Us>{}), ...);
+}
+
 constexpr int kBigSeg = 96;      // segments longer than this are expanded cooperatively
 constexpr int kSegQueue = 48;
 
@@ -618,87 +633,119 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     const int tb = T * B;
     const int cstride = kChunk * tb + 32;      // +32: lanes >= B read past their diagonal's block
 
-    float *cbuf0 = reinterpret_cast<float *>(smem_raw);
-    float *cbuf1 = cbuf0 + cstride;
-    int *bbuf0 = reinterpret_cast<int *>(cbuf1 + cstride);
-    int *bbuf1 = bbuf0 + kChunk;
+    // per chunk (double-buffered): the cost diagonals widened to fp64, and what the recurrence needs that does
+    // NOT depend on the recurrence - all produced by the staging warps, off the serial chain:
+    //   oc / ov  per (diagonal, lane): forced backpointer code + value (boundary nodes, nodes outside the
+    //            lattice, lanes >= B), kNoOvr where the recurrence decides
+    //   dl       per diagonal: [0] = boff(aa) - boff(aa-1); [s] = 8 * (boff(aa) - boff(aa-s)), s = 2..NH:
+    //            the lane shift of a predecessor on diagonal aa - s, as a byte offset into the csum ring
+    constexpr int kNoOvr = 0xFE;
+    constexpr int DLS = NH + 1;
+    constexpr int RS = 32 + K + NH + ((32 + K + NH) & 1);      // ring row: K pad | 32 lanes | NH pad, in doubles
+    double *cbuf0 = reinterpret_cast<double *>(smem_raw);
+    double *cbuf1 = cbuf0 + cstride;
+    double *ov0 = cbuf1 + cstride;
+    double *ov1 = ov0 + kChunk * 32;
+    double *ring = ov1 + kChunk * 32;                          // NH rows of RS doubles
+    int *dl0 = reinterpret_cast<int *>(ring + NH * RS);
+    int *dl1 = dl0 + kChunk * DLS;
+    uint8_t *oc0 = reinterpret_cast<uint8_t *>(dl1 + kChunk * DLS);
+    uint8_t *oc1 = oc0 + kChunk * 32;
+    // results of a chunk (csum, backpointer code per diagonal and lane): written by the recurrence with plain
+    // shared-memory stores, flushed to HBM (coalesced) by the staging warps while the next chunk runs
+    uint8_t *bpo0 = oc1 + kChunk * 32;
+    uint8_t *bpo1 = bpo0 + kChunk * 32;
+    double *cso0 = reinterpret_cast<double *>(bpo1 + kChunk * 32);      // 8-byte aligned: every block above is a multiple of 8 bytes
+    double *cso1 = cso0 + kChunk * 32;
     const double pen = *job.del_penalty;
     const float *g_costs = job.costs;
     const int32_t *g_ypath = job.ypath;
     uint8_t *g_bp = job.bp;
     double *g_csum = job.csum;
 
-    // chunk c = node diagonals [c*kChunk, (c+1)*kChunk); its cost diagonals (aa - 2) are one
-    // contiguous, 16-byte aligned run in HBM (kChunk*tb and 2*tb floats are multiples of 4 because
-    // the band width is even): copied with 16-byte cp.async, no register staging.
+    // chunk c = node diagonals [c*kChunk, (c+1)*kChunk); its cost diagonals (aa - 2) are one contiguous,
+    // 16-byte aligned run in HBM (kChunk is even and so is the band width, so kChunk*tb and 2*tb floats are
+    // multiples of 4): read as float4, stored as fp64 (the recurrence adds them to fp64 cumulative costs).
     auto stage = [&](int c, int first_thread, int nthreads) {
         const int start = c * kChunk;
-        float *cb = (c & 1) ? cbuf1 : cbuf0;
-        int *bb = (c & 1) ? bbuf1 : bbuf0;
+        double *cb = (c & 1) ? cbuf1 : cbuf0;
+        double *ov = (c & 1) ? ov1 : ov0;
+        int *dl = (c & 1) ? dl1 : dl0;
+        uint8_t *oc = (c & 1) ? oc1 : oc0;
         const int lo = start - 2, hi = min(start + kChunk, nodes_a) - 2;   // cost diagonals [lo, hi)
         const int clo = max(lo, 0), chi = min(hi, A);
         if (chi > clo) {
             const float *src = g_costs + (size_t)clo * tb;
-            float *dst = cb + (size_t)(clo - lo) * tb;
+            double *dst = cb + (size_t)(clo - lo) * tb;
             const int n = (chi - clo) * tb;
             const int n4 = n >> 2;
             for (int i = first_thread; i < n4; i += nthreads) {
-                const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + 4 * i);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(src + 4 * i));
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                reinterpret_cast<double2 *>(dst)[2 * i] = make_double2((double)v.x, (double)v.y);
+                reinterpret_cast<double2 *>(dst)[2 * i + 1] = make_double2((double)v.z, (double)v.w);
             }
-            for (int i = 4 * n4 + first_thread; i < n; i += nthreads) dst[i] = __ldg(src + i);
+            for (int i = 4 * n4 + first_thread; i < n; i += nthreads) dst[i] = (double)__ldg(src + i);
         }
-        for (int i = first_thread; i < kChunk; i += nthreads) {
-            const int aa = start + i;
-            bb[i] = aa < nodes_a ? svx_boff_out(g_ypath, aa, w) : 0;
+        for (int idx = first_thread; idx < kChunk * 32; idx += nthreads) {
+            const int i = idx >> 5, l = idx & 31, aa = start + i;
+            int code = SVX_BP_NONE;
+            double val = INFINITY;
+            if (aa < nodes_a && l < B) {
+                const int yy = l + svx_boff_out(g_ypath, aa, w), xx = aa - yy;
+                // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the deletions -
+                // reference quirk, dp_core.pyx:382,390; its anti-diagonal aa - 2 < A always holds for aa <= A + 1)
+                if ((unsigned)(xx - 1) < (unsigned)s0 && (unsigned)(yy - 1) < (unsigned)s1) code = kNoOvr;
+                else if (xx == 0 && yy >= 0 && yy <= s1) { val = __dmul_rn(pen, (double)yy); code = T; }        // bp (0,1)
+                else if (yy == 0 && xx >= 0 && xx <= s0) { val = __dmul_rn(pen, (double)xx); code = T + 1; }    // bp (1,0)
+            }
+            oc[idx] = (uint8_t)code;
+            ov[idx] = val;
         }
-        asm volatile("cp.async.commit_group;\n" ::);
-        asm volatile("cp.async.wait_group 0;\n" ::);
+        for (int idx = first_thread; idx < kChunk * DLS; idx += nthreads) {
+            const int i = idx / DLS, sft = idx % DLS, aa = start + i;
+            const int back = sft == 0 ? 1 : sft;
+            int d = 0;
+            if (aa < nodes_a && sft != 1) {
+                // diagonals before the first one count as offset 0 (they only ever hold +inf)
+                d = svx_boff_out(g_ypath, aa, w) - (aa - back >= 0 ? svx_boff_out(g_ypath, aa - back, w) : 0);
+                if (sft) d = min(max(d, -K), NH) * 8;       // inside the ring row's padding whatever the path does
+            }
+            dl[idx] = d;
+        }
+    };
+
+    auto flush = [&](int c, int first_thread, int nthreads) {
+        const int start = c * kChunk;
+        const int n = min(kChunk, nodes_a - start) * B;
+        const double *cso = (c & 1) ? cso1 : cso0;
+        const uint8_t *bpo = (c & 1) ? bpo1 : bpo0;
+        double *gc = g_csum + (size_t)start * B;
+        uint8_t *gb = g_bp + (size_t)start * B;
+        for (int idx = first_thread; idx < n; idx += nthreads) {
+            const int i = idx / B, b = idx - i * B;
+            gc[idx] = cso[i * 32 + b];
+            gb[idx] = bpo[i * 32 + b];
+        }
     };
 
     // ---- phase 1 ------------------------------------------------------------------------------
-    // Lanes >= B always hold +inf, and so do lattice nodes outside the documents, so a predecessor
-    // outside the node band (source lane < 0 wraps to a lane >= B since B + K <= 32 - 1) or with a
-    // negative coordinate contributes +inf and can never win the strict '<': no range tests in the
-    // candidate loop.
-    double hist[NH + 1];     // hist[s] = csum of this lane's slot on diagonal aa - s (s >= 1)
-    int bofh[NH + 1];        // bofh[s] = b_offset_out[aa - s]
-#pragma unroll
-    for (int s = 0; s <= NH; ++s) { hist[s] = INFINITY; bofh[s] = 0; }
-
-    // Everything about diagonal a_t that does not depend on the diagonal right before it: band
-    // geometry, the boundary / out-of-lattice override, and the best alignment-type candidate (types
-    // reach back >= 2 diagonals).  HOFF = 1 when called one diagonal ahead (history registers still
-    // describe a_t - 1 as "current").  Two independent strict-'<' chains (first / second half of the
-    // type list) halve the dependent compare-select latency and keep the first-minimum tie-break.
-    const int s0_l = lane < B ? s0 : 0, s1_l = lane < B ? s1 : 0;
-    struct Prep {
-        double tbest, ovr_val;     // best type candidate; value forced when `ovr`
-        int tcode, ovr_code, d1, bo;
-        bool ovr;
-    };
-    auto prepare = [&](auto hoff_tag, int a_t, int bo_t, int bo_prev, const float *crow) {
-        constexpr int HOFF = decltype(hoff_tag)::value;
-        constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
-        Prep p;
-        p.bo = bo_t;
-        p.d1 = bo_t - bo_prev;
-        const int yy = lane + bo_t, xx = a_t - yy;
-        // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the deletions -
-        // reference quirk, dp_core.pyx:382,390; its anti-diagonal a_t - 2 < A always holds for a_t <= A + 1);
-        // lanes >= B and lattice nodes outside the documents hold +inf, so predecessors outside the node band
-        // never win the strict '<' (no range tests below).  s0_l / s1_l are 0 for lanes >= B.
-        const bool cell_ok = (unsigned)(xx - 1) < (unsigned)s0_l && (unsigned)(yy - 1) < (unsigned)s1_l;
-        p.ovr = !cell_ok;
-        p.ovr_val = INFINITY;
-        p.ovr_code = SVX_BP_NONE;
-        // boundary nodes (xx == 0 or yy == 0) only occur while the band touches an edge of the lattice
-        const bool by = lane < B && xx == 0 && yy >= 0 && yy <= s1;           // csum = pen * yy, bp (0,1)
-        const bool bx = lane < B && !by && yy == 0 && xx >= 0 && xx <= s0;    // csum = pen * xx, bp (1,0)
-        if (__any_sync(0xffffffffu, by || bx)) {
-            if (by) { p.ovr_val = __dmul_rn(pen, (double)yy); p.ovr_code = T; }
-            else if (bx) { p.ovr_val = __dmul_rn(pen, (double)xx); p.ovr_code = T + 1; }
-        }
+    // The fp64 cumulative costs of the last NH diagonals live in a shared-memory ring with COMPILE-TIME
+    // rows: chunks hold whole groups of NH diagonals (kChunk % NH == 0), diagonal i of a chunk uses row
+    // i % NH, and the group loop is fully unrolled.  A type candidate (x,y) is then one add (lane byte offset
+    // + dl[x+y]) and one LDS.64 of the predecessor, one LDS.64 of the cost, DADD, compare-select; the rows
+    // are padded with +inf on both sides and lanes >= B / lattice nodes outside the documents are forced to
+    // +inf, so predecessors outside the node band never win the strict '<' - no range tests.  Candidates of
+    // diagonal aa + 1 (they reach back >= 2 diagonals) are evaluated BEFORE the chain of diagonal aa:
+    // csum(aa-1) -> + pen -> two 64-bit shuffles -> two compare-selects -> forced value -> csum(aa).
+    // Two independent strict-'<' chains (first / second half of the type list) halve the dependent
+    // compare-select latency and keep the first-minimum tie-break.
+    for (int i = tid; i < NH * RS; i += blockDim.x) ring[i] = INFINITY;
+    constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
+    const char *ring_lane = reinterpret_cast<const char *>(ring + K + lane);
+    auto types = [&](auto slot_tag, const double *cb, const int *dl, int i, double &tbest, int &tcode) {
+        constexpr int U = decltype(slot_tag)::value;          // ring row of diagonal i
+        const double *crow = cb + (size_t)i * tb + lane;
+        const int *dli = dl + i * DLS;
         double b0 = INFINITY, b1 = INFINITY;
         int c0 = SVX_BP_NONE, c1 = SVX_BP_NONE;
         int t = 0;
@@ -706,65 +753,77 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
         for (int x = 1; x <= K; ++x) {
 #pragma unroll
             for (int y = 1; x + y <= K + 1; ++y, ++t) {
-                const int s = x + y;                       // >= 2, so s - HOFF >= 1
-                const int src = lane + (bo_t - bofh[s - HOFF]) - y;
-                const double pv = __shfl_sync(0xffffffffu, hist[s - HOFF], src);
-                const double tot = __dadd_rn(pv, (double)crow[t * B]);
+                const int sft = x + y;                                       // >= 2
+                const int row = (U - sft + 2 * NH) % NH;
+                const double pv = *reinterpret_cast<const double *>(ring_lane + dli[sft] + (row * RS - y) * 8);
+                const double tot = __dadd_rn(pv, crow[t * B]);
                 if (t < SPLIT) { if (tot < b0) { b0 = tot; c0 = t; } }
                 else { if (tot < b1) { b1 = tot; c1 = t; } }
             }
         }
         if (SPLIT < T && b1 < b0) { b0 = b1; c0 = c1; }
-        p.tbest = b0; p.tcode = c0;
-        return p;
+        tbest = b0; tcode = c0;
     };
-    using Tag0 = std::integral_constant<int, 0>;
-    using Tag1 = std::integral_constant<int, 1>;
 
     const int nchunks = (nodes_a + kChunk - 1) / kChunk;
+#ifdef SVX_DP_TIMING
+    long long tm0 = clock64(), tm1 = 0, tm2 = 0;
+#endif
     stage(0, tid, blockDim.x);
     __syncthreads();
+    double prev = INFINITY;                       // csum of the previous diagonal, this lane
     for (int c = 0; c < nchunks; ++c) {
         if (warp != 0) {
+            if (c >= 1) flush(c - 1, tid - 32, blockDim.x - 32);
             if (c + 1 < nchunks) stage(c + 1, tid - 32, blockDim.x - 32);
         } else {
-            const float *cb = (c & 1) ? cbuf1 : cbuf0;
-            const int *bo = (c & 1) ? bbuf1 : bbuf0;
+            const double *cb = (c & 1) ? cbuf1 : cbuf0;
+            const double *ov = ((c & 1) ? ov1 : ov0) + lane;
+            const uint8_t *oc = ((c & 1) ? oc1 : oc0) + lane;
+            const int *dl = (c & 1) ? dl1 : dl0;
             const int start = c * kChunk;
-            const int end = min(start + kChunk, nodes_a);
-            uint8_t *bp_out = g_bp + (size_t)start * B + lane;
-            double *cs_out = g_csum + (size_t)start * B + lane;
-            Prep cur = prepare(Tag0{}, start, bo[0], bofh[1], cb + lane);
-            for (int aa = start; aa < end; ++aa) {
-                // software pipeline: diagonal aa+1 is prepared here, beside the latency chain of aa
-                Prep nxt = cur;
-                if (aa + 1 < end)
-                    nxt = prepare(Tag1{}, aa + 1, bo[aa + 1 - start], cur.bo, cb + (size_t)(aa + 1 - start) * tb + lane);
-                // the chain: csum(aa-1) -> + pen -> shuffle -> two compare-selects -> override -> csum(aa)
-                double best = cur.tbest;
-                int code = cur.tcode;
-                const double hp = __dadd_rn(hist[1], pen);
-                double tot = __shfl_sync(0xffffffffu, hp, lane + cur.d1 - 1);        // (0,1): consume y
-                if (tot < best) { best = tot; code = T; }
-                tot = __shfl_sync(0xffffffffu, hp, lane + cur.d1);                   // (1,0): consume x
-                if (tot < best) { best = tot; code = T + 1; }
-                if (cur.ovr) { best = cur.ovr_val; code = cur.ovr_code; }
-                if (lane < B) {
-                    *bp_out = (uint8_t)code;
-                    *cs_out = best;
-                }
-                bp_out += B; cs_out += B;
-#pragma unroll
-                for (int s = NH; s >= 2; --s) { hist[s] = hist[s - 1]; bofh[s] = bofh[s - 1]; }
-                hist[1] = best;
-                bofh[1] = cur.bo;
-                cur = nxt;
+            const int ndiag = min(kChunk, nodes_a - start);
+            uint8_t *bp_out = ((c & 1) ? bpo1 : bpo0) + lane;
+            double *cs_out = ((c & 1) ? cso1 : cso0) + lane;
+            double tbest, nbest = INFINITY;
+            int tcode, ncode = SVX_BP_NONE;
+            types(std::integral_constant<int, 0>{}, cb, dl, 0, tbest, tcode);
+            for (int g = 0; g < ndiag; g += NH) {
+                const bool group_follows = g + NH < kChunk;
+                auto step = [&](auto u_tag) {
+                    constexpr int u = decltype(u_tag)::value;
+                    const int i = g + u;                       // diagonals past the end compute on padding; not stored
+                    if (u + 1 < NH || group_follows)
+                        types(std::integral_constant<int, (u + 1) % NH>{}, cb, dl, i + 1, nbest, ncode);
+                    double best = tbest;
+                    int code = tcode;
+                    const double hp = __dadd_rn(prev, pen);
+                    const int d1 = dl[i * DLS];
+                    double tot = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);        // (0,1): consume y
+                    if (tot < best) { best = tot; code = T; }
+                    tot = __shfl_sync(0xffffffffu, hp, lane + d1);                   // (1,0): consume x
+                    if (tot < best) { best = tot; code = T + 1; }
+                    const int forced = oc[i * 32];
+                    if (forced != kNoOvr) { best = ov[i * 32]; code = forced; }
+                    bp_out[i * 32] = (uint8_t)code;
+                    cs_out[i * 32] = best;
+                    ring[u * RS + K + lane] = best;
+                    __syncwarp();
+                    prev = best;
+                    tbest = nbest; tcode = ncode;
+                };
+                svx_static_for(step, std::make_integer_sequence<int, NH>{});
             }
         }
         __syncthreads();
     }
+    flush(nchunks - 1, tid, blockDim.x);
+    __syncthreads();
 
     // ---- phase 2: backpointer walk through a shared-memory window ---------------------------------
+#ifdef SVX_DP_TIMING
+    tm1 = clock64();
+#endif
     int *wboff = reinterpret_cast<int *>(smem_raw);
     uint8_t *wbp = reinterpret_cast<uint8_t *>(wboff + ((win_diags + 8 + 3) & ~3));     // 16-byte aligned
     const int cap = job.rec_cap;
@@ -823,6 +882,9 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     }
 
     // ---- phase 3: scores and the next level's search path -------------------------------------------
+#ifdef SVX_DP_TIMING
+    tm2 = clock64();
+#endif
     const int n = min(wst[2], cap), status = wst[3];
     SvxAlignRec *recs = job.recs + (cap - n);                // document order
     for (int i = tid; i < n; i += blockDim.x) {
@@ -878,6 +940,12 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
         *job.status_d = status;
         if (job.nrecs) *job.nrecs = wst[2];
     }
+#ifdef SVX_DP_TIMING
+    __syncthreads();
+    if (tid == 0 && blockIdx.x == 0)
+        printf("dp_tri<%d> A=%d: recurrence %lld, walk %lld, scores+path %lld cycles (%d records)\n", K, A, tm1 - tm0, tm2 - tm1,
+               clock64() - tm2, n);
+#endif
 }
 
 inline bool is_standard_types(const SvxBandJob &j, int *k_out)
@@ -1011,10 +1079,20 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
 {
     constexpr int T = K * (K + 1) / 2;
     const int tb = T * bmax;
-    int chunk = (int)((64 * 1024) / ((size_t)2 * tb * sizeof(float)));
-    chunk = chunk > kMaxChunk ? kMaxChunk : (chunk < 4 ? 4 : chunk);
-    chunk &= ~1;       // even: chunk * tb floats is then a multiple of 4 (B is even), the 16-byte cp.async staging relies on it
-    const size_t dp_bytes = (size_t)2 * (chunk * tb + 32) * sizeof(float) + (size_t)2 * chunk * sizeof(int);
+    constexpr int NH = K + 1;
+    // chunk: as many diagonals as ~96 KB of fp64 cost buffers hold (at most kMaxChunk), a multiple of NH (the
+    // recurrence's csum ring has compile-time rows) and even (16-byte staging loads: chunk * tb floats must
+    // be a multiple of 4, B is even)
+    constexpr int STEP = (NH % 2) ? 2 * NH : NH;
+    constexpr int RS = 32 + K + NH + ((32 + K + NH) & 1);
+    int chunk = (int)((96 * 1024) / ((size_t)2 * tb * sizeof(double)));
+    chunk = chunk > kMaxChunk ? kMaxChunk : chunk;
+    chunk = chunk / STEP * STEP;
+    if (chunk < STEP) chunk = STEP;
+    const size_t dp_bytes = (size_t)2 * (chunk * tb + 32) * sizeof(double) + (size_t)2 * chunk * 32 * sizeof(double) +
+                            (size_t)NH * RS * sizeof(double) + (size_t)2 * chunk * (NH + 1) * sizeof(int) + (size_t)2 * chunk * 32 +
+                            (size_t)2 * chunk * 32 + (size_t)2 * chunk * 32 * sizeof(double) + 16;
+    if (dp_bytes > 220 * 1024) return -1;
     // walk window: whole job when it fits in ~96 KB, otherwise 96 KB windows
     const int per_diag = bmax + (int)sizeof(int);
     int win = amax_len + 2;

@@ -122,3 +122,67 @@ def test_filter_by_cost_known_answer():
     want = open(os.path.join(ex, "shipped_align_0.7.txt")).read().splitlines()
     got = [f"{xs}:{ys}:{c}" for xs, ys, c in kept]
     assert got == want
+
+
+def _synthetic_corpus(root, n_docs, k, rng):
+    """A step-5.3 style tree for n_docs document pairs: segment lists '<start> <end>', the concatenation keys
+    of every (start_i, end_{i+j}), j < k, in shuffled order, and raw fp16 .embed files (--fp16_embed)."""
+    from speech_vecalign_b200 import synth
+    meta = []
+    for d in range(n_docs):
+        n0 = int(rng.integers(3, 420))
+        n1 = max(1, int(n0 * rng.uniform(0.7, 1.4)))
+        vecs = synth.synth_pair(n0, n1, k, seed=900 + d)
+        for lang, v in zip(("en", "de"), vecs):
+            n = v.shape[1]
+            bounds = np.cumsum(rng.integers(1600, 64000, size=n + 1))
+            (root / "segments" / lang).mkdir(parents=True, exist_ok=True)
+            (root / "cat_segs" / lang).mkdir(parents=True, exist_ok=True)
+            (root / "embeds" / lang).mkdir(parents=True, exist_ok=True)
+            (root / "segments" / lang / f"doc{d}_{lang}.txt").write_text(
+                "".join(f"{bounds[i]} {bounds[i + 1]}\n" for i in range(n)))
+            keys, rows = [], []
+            for i in range(n):
+                for j in range(k):
+                    if i + j < n:
+                        keys.append(f"{bounds[i]} {bounds[i + j + 1]}")
+                        rows.append(v[j, i + j])
+            order = rng.permutation(len(keys))
+            (root / "cat_segs" / lang / f"doc{d}_{lang}.txt").write_text("".join(keys[o] + "\n" for o in order))
+            np.stack([rows[o] for o in order]).astype(np.float16).tofile(root / "embeds" / lang / f"doc{d}_{lang}.embed")
+        meta.append(f"/a/en/doc{d}_en.ogg\t/a/de/doc{d}_de.ogg")
+    (root / "metadata.tsv").write_text("\n".join(meta) + "\n")
+    return [str(root / "metadata.tsv"), str(root / "out"), "--src_lang", "en", "--tgt_lang", "de", "--seg_dir",
+            str(root / "segments"), "--concat_dir", str(root / "cat_segs"), "--embed_dir", str(root / "embeds"),
+            "--fp16_embed", "-a", str(k + 1), "--max_size_full_dp", "100", "--costs_sample_size", "4000"]
+
+
+@pytest.mark.gpu
+def test_driver_batches_and_shards_synthetic_corpus(tmp_path, oracle):
+    """Nine synthetic document pairs through the driver: small --batch_gb (several GPU batches), two shards
+    (--rank/--n_shard), --skip_existing; every output file equals the oracle run on the same host-built
+    tensors with the pair's seed, whatever the batching or sharding."""
+    import math
+    from speech_vecalign_b200 import seg_align
+    from speech_vecalign_b200.vecalign import read_alignments
+    k = 3
+    argv = _synthetic_corpus(tmp_path, 9, k, np.random.default_rng(5))
+    assert seg_align.main(argv + ["--batch_gb", "0.004"]) == 9
+    out_dir = tmp_path / "out" / "en-de"
+    first = {p.name: p.read_text() for p in sorted(out_dir.iterdir())}
+    assert len(first) == 9
+    # the same corpus in two shards and one big batch: identical files
+    for p in out_dir.iterdir():
+        p.unlink()
+    done = [seg_align.main(argv + ["--rank", str(r), "--n_shard", "2"]) for r in range(2)]
+    assert sum(done) == 9 and min(done) >= 1
+    assert {p.name: p.read_text() for p in sorted(out_dir.iterdir())} == first
+    assert seg_align.main(argv + ["--skip_existing"]) == 0
+    # against the oracle on host-gathered tensors, seeded like the driver seeds its pairs
+    args = seg_align.build_parser().parse_args(argv)
+    _, jobs = seg_align.resolve_pairs(open(args.metadata), args)
+    for item in jobs[:4]:
+        v0, v1 = seg_align.load_pair(item, k, args, on_device=False)
+        np.random.seed(seg_align.pair_seed(item, 0))
+        ref = oracle.vecalign(v0, v1, oracle.alignment_types(k + 1), 0.2, math.ceil(k / 2) + 5, 100, 4000, 100, fast_host=True)
+        assert same_alignments(read_alignments(str(item["out"])), ref[0]["final_alignments"])
