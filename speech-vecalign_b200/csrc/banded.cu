@@ -742,7 +742,8 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     for (int i = tid; i < NH * RS; i += blockDim.x) ring[i] = INFINITY;
     constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
     const char *ring_lane = reinterpret_cast<const char *>(ring + K + lane);
-    auto types = [&](auto slot_tag, const double *cb, const int *dl, int i, double &tbest, int &tcode) {
+    struct Cand { double best; int code; };
+    auto types = [&](auto slot_tag, const double *cb, const int *dl, int i) -> Cand {
         constexpr int U = decltype(slot_tag)::value;          // ring row of diagonal i
         const double *crow = cb + (size_t)i * tb + lane;
         const int *dli = dl + i * DLS;
@@ -762,7 +763,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             }
         }
         if (SPLIT < T && b1 < b0) { b0 = b1; c0 = c1; }
-        tbest = b0; tcode = c0;
+        return Cand{b0, c0};
     };
 
     const int nchunks = (nodes_a + kChunk - 1) / kChunk;
@@ -785,18 +786,15 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             const int ndiag = min(kChunk, nodes_a - start);
             uint8_t *bp_out = ((c & 1) ? bpo1 : bpo0) + lane;
             double *cs_out = ((c & 1) ? cso1 : cso0) + lane;
-            double tbest, nbest = INFINITY;
-            int tcode, ncode = SVX_BP_NONE;
-            types(std::integral_constant<int, 0>{}, cb, dl, 0, tbest, tcode);
+            Cand cur = types(std::integral_constant<int, 0>{}, cb, dl, 0), nxt = cur;
             for (int g = 0; g < ndiag; g += NH) {
                 const bool group_follows = g + NH < kChunk;
                 auto step = [&](auto u_tag) {
                     constexpr int u = decltype(u_tag)::value;
                     const int i = g + u;                       // diagonals past the end compute on padding; not stored
-                    if (u + 1 < NH || group_follows)
-                        types(std::integral_constant<int, (u + 1) % NH>{}, cb, dl, i + 1, nbest, ncode);
-                    double best = tbest;
-                    int code = tcode;
+                    if (u + 1 < NH || group_follows) nxt = types(std::integral_constant<int, (u + 1) % NH>{}, cb, dl, i + 1);
+                    double best = cur.best;
+                    int code = cur.code;
                     const double hp = __dadd_rn(prev, pen);
                     const int d1 = dl[i * DLS];
                     double tot = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);        // (0,1): consume y
@@ -810,7 +808,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
                     ring[u * RS + K + lane] = best;
                     __syncwarp();
                     prev = best;
-                    tbest = nbest; tcode = ncode;
+                    cur = nxt;
                 };
                 svx_static_for(step, std::make_integer_sequence<int, NH>{});
             }
