@@ -743,10 +743,16 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     constexpr int SPLIT = T >= 6 ? (T + 1) / 2 : T;
     const char *ring_lane = reinterpret_cast<const char *>(ring + K + lane);
     struct Cand { double best; int code; };
-    auto types = [&](auto slot_tag, const double *cb, const int *dl, int i) -> Cand {
+    struct Shifts { int v[NH + 1]; };                            // dl row of one diagonal, in registers
+    auto load_shifts = [&](const int *dl, int i) {
+        Shifts sh;
+#pragma unroll
+        for (int q = 0; q <= NH; ++q) sh.v[q] = (q == 1) ? 0 : dl[i * DLS + q];
+        return sh;
+    };
+    auto types = [&](auto slot_tag, const double *cb, const Shifts &sh, int i) -> Cand {
         constexpr int U = decltype(slot_tag)::value;          // ring row of diagonal i
         const double *crow = cb + (size_t)i * tb + lane;
-        const int *dli = dl + i * DLS;
         double b0 = INFINITY, b1 = INFINITY;
         int c0 = SVX_BP_NONE, c1 = SVX_BP_NONE;
         int t = 0;
@@ -756,7 +762,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             for (int y = 1; x + y <= K + 1; ++y, ++t) {
                 const int sft = x + y;                                       // >= 2
                 const int row = (U - sft + 2 * NH) % NH;
-                const double pv = *reinterpret_cast<const double *>(ring_lane + dli[sft] + (row * RS - y) * 8);
+                const double pv = *reinterpret_cast<const double *>(ring_lane + sh.v[sft] + (row * RS - y) * 8);
                 const double tot = __dadd_rn(pv, crow[t * B]);
                 if (t < SPLIT) { if (tot < b0) { b0 = tot; c0 = t; } }
                 else { if (tot < b1) { b1 = tot; c1 = t; } }
@@ -786,29 +792,41 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             const int ndiag = min(kChunk, nodes_a - start);
             uint8_t *bp_out = ((c & 1) ? bpo1 : bpo0) + lane;
             double *cs_out = ((c & 1) ? cso1 : cso0) + lane;
-            Cand cur = types(std::integral_constant<int, 0>{}, cb, dl, 0), nxt = cur;
+            // software pipeline: everything of diagonal i + 1 that does not depend on csum(i) is loaded / evaluated
+            // while the shuffles of diagonal i are in flight
+            Shifts sh = load_shifts(dl, 0);
+            Cand cur = types(std::integral_constant<int, 0>{}, cb, sh, 0), nxt = cur;
+            int fcode = oc[0];
+            double fval = ov[0];
             for (int g = 0; g < ndiag; g += NH) {
                 const bool group_follows = g + NH < kChunk;
                 auto step = [&](auto u_tag) {
                     constexpr int u = decltype(u_tag)::value;
                     const int i = g + u;                       // diagonals past the end compute on padding; not stored
-                    if (u + 1 < NH || group_follows) nxt = types(std::integral_constant<int, (u + 1) % NH>{}, cb, dl, i + 1);
+                    const bool more = u + 1 < NH || group_follows;          // diagonal i + 1 is in this chunk
+                    const int d1 = sh.v[0];
+                    const double hp = __dadd_rn(prev, pen);
+                    const double ty = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);   // (0,1): consume y
+                    const double tx = __shfl_sync(0xffffffffu, hp, lane + d1);       // (1,0): consume x
+                    int ncode = fcode;
+                    double nval = fval;
+                    if (more) {
+                        sh = load_shifts(dl, i + 1);
+                        ncode = oc[(i + 1) * 32];
+                        nval = ov[(i + 1) * 32];
+                        nxt = types(std::integral_constant<int, (u + 1) % NH>{}, cb, sh, i + 1);
+                    }
                     double best = cur.best;
                     int code = cur.code;
-                    const double hp = __dadd_rn(prev, pen);
-                    const int d1 = dl[i * DLS];
-                    double tot = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);        // (0,1): consume y
-                    if (tot < best) { best = tot; code = T; }
-                    tot = __shfl_sync(0xffffffffu, hp, lane + d1);                   // (1,0): consume x
-                    if (tot < best) { best = tot; code = T + 1; }
-                    const int forced = oc[i * 32];
-                    if (forced != kNoOvr) { best = ov[i * 32]; code = forced; }
+                    if (ty < best) { best = ty; code = T; }
+                    if (tx < best) { best = tx; code = T + 1; }
+                    if (fcode != kNoOvr) { best = fval; code = fcode; }
                     bp_out[i * 32] = (uint8_t)code;
                     cs_out[i * 32] = best;
                     ring[u * RS + K + lane] = best;
                     __syncwarp();
                     prev = best;
-                    cur = nxt;
+                    cur = nxt; fcode = ncode; fval = nval;
                 };
                 svx_static_for(step, std::make_integer_sequence<int, NH>{});
             }
