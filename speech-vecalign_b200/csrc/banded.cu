@@ -617,6 +617,25 @@ __device__ __forceinline__ void emit_segment(SegQueue *q, int32_t *ypath, int pa
     emit_points(ypath, path_len, xs, ys, xw, yw, 1, 1);
 }
 
+// backpointer code of the standard type set -> dx | dy << 4
+__host__ __device__ constexpr int svx_dec_code(int K, int code)
+{
+    const int T = K * (K + 1) / 2;
+    if (code == T) return 0 | (1 << 4);
+    if (code == T + 1) return 1 | (0 << 4);
+    int xq = 1, rem = code;
+    while (rem >= K + 1 - xq) { rem -= K + 1 - xq; ++xq; }
+    return xq | ((rem + 1) << 4);
+}
+__host__ __device__ constexpr unsigned long long svx_dec_packed(int K, int first)
+{
+    const int T = K * (K + 1) / 2;
+    unsigned long long v = 0;
+    for (int code = first; code < T + 2 && code < first + 8; ++code)
+        v |= (unsigned long long)svx_dec_code(K, code) << (8 * (code - first));
+    return v;
+}
+
 template <int K>
 __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, int kChunk, int win_diags)
 {
@@ -625,6 +644,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wst[5];                     // walk state: x, y, count, status, done
     __shared__ SegQueue segq;
+    __shared__ uint8_t tdec[SVX_MAX_TYPES + 2];
     const SvxBandJob &job = jobs[blockIdx.x];
     const int B = job.band, A = job.a_len, w = job.width_over2;
     const int s0 = job.s0, s1 = job.s1;
@@ -778,7 +798,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 #endif
     stage(0, tid, blockDim.x);
     __syncthreads();
-    double prev = INFINITY;                       // csum of the previous diagonal, this lane
+    double prev = INFINITY, prev2 = INFINITY;     // csum of the previous two diagonals, this lane
     for (int c = 0; c < nchunks; ++c) {
         if (warp != 0) {
             if (c >= 1) flush(c - 1, tid - 32, blockDim.x - 32);
@@ -796,6 +816,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             // while the shuffles of diagonal i are in flight
             Shifts sh = load_shifts(dl, 0);
             Cand cur = types(std::integral_constant<int, 0>{}, cb, sh, 0), nxt = cur;
+            double cost1 = cb[lane];                              // K == 1: cost of the chunk's first diagonal
             int fcode = oc[0];
             double fval = ov[0];
             for (int g = 0; g < ndiag; g += NH) {
@@ -805,6 +826,36 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
                     const int i = g + u;                       // diagonals past the end compute on padding; not stored
                     const bool more = u + 1 < NH || group_follows;          // diagonal i + 1 is in this chunk
                     const int d1 = sh.v[0];
+                    if constexpr (K == 1) {
+                        // coarse levels, one type (1,1): its predecessor csum(i-2) is still in a register, so the
+                        // whole step runs on shuffles - no ring traffic, no __syncwarp
+                        const double hp = __dadd_rn(prev, pen);
+                        const double p11 = __shfl_sync(0xffffffffu, prev2, lane + (sh.v[2] >> 3) - 1);
+                        const double ty = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);
+                        const double tx = __shfl_sync(0xffffffffu, hp, lane + d1);
+                        const double cost = cost1;
+                        int ncode = fcode;
+                        double nval = fval;
+                        if (more) {
+                            sh = load_shifts(dl, i + 1);
+                            ncode = oc[(i + 1) * 32];
+                            nval = ov[(i + 1) * 32];
+                            cost1 = cb[(size_t)(i + 1) * tb + lane];
+                        }
+                        double best = INFINITY;
+                        int code = SVX_BP_NONE;
+                        const double t11 = __dadd_rn(p11, cost);
+                        if (t11 < best) { best = t11; code = 0; }
+                        if (ty < best) { best = ty; code = T; }
+                        if (tx < best) { best = tx; code = T + 1; }
+                        if (fcode != kNoOvr) { best = fval; code = fcode; }
+                        bp_out[i * 32] = (uint8_t)code;
+                        cs_out[i * 32] = best;
+                        prev2 = prev;
+                        prev = best;
+                        fcode = ncode; fval = nval;
+                        return;
+                    }
                     const double hp = __dadd_rn(prev, pen);
                     const double ty = __shfl_sync(0xffffffffu, hp, lane + d1 - 1);   // (0,1): consume y
                     const double tx = __shfl_sync(0xffffffffu, hp, lane + d1);       // (1,0): consume x
@@ -843,6 +894,10 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     int *wboff = reinterpret_cast<int *>(smem_raw);
     uint8_t *wbp = reinterpret_cast<uint8_t *>(wboff + ((win_diags + 8 + 3) & ~3));     // 16-byte aligned
     const int cap = job.rec_cap;
+    SvxAlignRec *const recs_top = job.recs + (cap - 1);      // in a register: the walk's stores must not reload the descriptor
+    // backpointer code -> dx | dy << 4 (types x outer, y inner: row x holds K+1-x types; then (0,1), (1,0))
+    constexpr unsigned long long kDecPacked = svx_dec_packed(K, 0), kDecPackedHi = svx_dec_packed(K, 8);
+    for (int code = tid; code < T + 2; code += blockDim.x) tdec[code] = (uint8_t)svx_dec_code(K, code);
     if (tid == 0) {
         wst[0] = s0; wst[1] = s1; wst[2] = 0;
         wst[3] = (s0 + s1 >= nodes_a) ? SVX_ST_LEFT_BAND : SVX_ST_OK;
@@ -863,33 +918,44 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
         for (int i = (n16 << 4) + tid; i < nbytes; i += blockDim.x) wbp[i] = bsrc[i];
         __syncthreads();
         if (tid == 0) {
+            // One thread chases the backpointers.  Per step the dependent chain is: LDS backpointer code ->
+            // (dx,dy) decode (a shift of a packed constant for T + 2 <= 16, else one LDS of a table) -> band
+            // offset of the predecessor's diagonal -> new window index.  A warp does not speculate past a
+            // branch, so every way out of the loop shares ONE branch (measured: 6 exits 280 -> 1 exit 220
+            // cycles per record at K = 1; `volatile` / hoisted offset loads were slower).
             int x = wst[0], y = wst[1], cnt = wst[2], st = SVX_ST_OK;
-            int a = x + y;
-            int b = y - wboff[a - lo];
+            int ai = x + y - lo;                              // window row of the current node
+            int b = y - wboff[ai];
             if (b < 0 || b >= B) st = SVX_ST_LEFT_BAND;
-            while (st == SVX_ST_OK && !(x == 0 && y == 0)) {
-                const int code = wbp[(a - lo) * B + b];
-                if (code > T + 1) { st = SVX_ST_NO_BACKPTR; break; }
-                int dx, dy;
-                if (code == T) { dx = 0; dy = 1; }
-                else if (code == T + 1) { dx = 1; dy = 0; }
-                else {            // x outer, y inner: row x holds K+1-x types
-                    int xq = 1, rem = code;
-                    while (rem >= K + 1 - xq) { rem -= K + 1 - xq; ++xq; }
-                    dx = xq; dy = rem + 1;
-                }
+            while (st == SVX_ST_OK && (x | y) != 0) {
+                const int code = wbp[ai * B + b];
+                int wo[NH];
+#pragma unroll
+                for (int q = 0; q < NH; ++q) wo[q] = wboff[max(ai - 1 - q, 0)];
+                int dd;
+                if constexpr (T + 2 <= 8) dd = (int)(kDecPacked >> (8 * (code & 7))) & 0xff;
+                else if constexpr (T + 2 <= 16) dd = (int)((code < 8 ? kDecPacked : kDecPackedHi) >> (8 * (code & 7))) & 0xff;
+                else dd = tdec[code & 127];
+                const int dx = dd & 15, dy = dd >> 4;
                 const int px = x - dx, py = y - dy;
-                if (px < 0 || py < 0) { st = SVX_ST_LEFT_BAND; break; }      // reference: 'traceback bug'
-                const int pa = px + py;
-                if (pa < lo) break;                                          // window exhausted
-                const int pb = py - wboff[pa - lo];
-                if (pb < 0 || pb >= B) { st = SVX_ST_LEFT_BAND; break; }
+                const int sft = dx + dy;
+                int pw = wo[0];
+#pragma unroll
+                for (int q = 1; q < NH; ++q) pw = (sft == q + 1) ? wo[q] : pw;
+                const int pb = py - pw;
+                // one branch for every way out (a warp does not speculate past a branch): classified afterwards
+                if ((code > T + 1) | ((px | py) < 0) | (ai - sft < 0) | ((unsigned)pb >= (unsigned)B)) {
+                    if (code > T + 1) st = SVX_ST_NO_BACKPTR;
+                    else if ((px | py) < 0) st = SVX_ST_LEFT_BAND;           // reference: 'traceback bug'
+                    else if (ai - sft >= 0) st = SVX_ST_LEFT_BAND;           // else: window exhausted, reload
+                    break;
+                }
                 if (cnt < cap) {
-                    int *r = reinterpret_cast<int *>(job.recs + (cap - 1 - cnt));
-                    r[0] = x; r[1] = y; r[2] = dx; r[3] = dy;
+                    int2 *r = reinterpret_cast<int2 *>(recs_top - cnt);
+                    r[0] = make_int2(x, y); r[1] = make_int2(dx, dy);
                 } else st |= SVX_ST_OVERFLOW;
                 ++cnt;
-                x = px; y = py; a = pa; b = pb;
+                x = px; y = py; ai -= sft; b = pb;
             }
             wst[0] = x; wst[1] = y; wst[2] = cnt; wst[3] = st;
             wst[4] = (st != SVX_ST_OK) || (x == 0 && y == 0);
