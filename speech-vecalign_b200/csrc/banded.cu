@@ -636,8 +636,10 @@ __host__ __device__ constexpr unsigned long long svx_dec_packed(int K, int first
     return v;
 }
 
+constexpr int kDpThreads = 256;      // warp 0 = recurrence, 7 staging warps (their work is global-load latency)
+
 template <int K>
-__global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, int kChunk, int win_diags)
+__global__ void __launch_bounds__(kDpThreads) k_banded_dp_tri(const SvxBandJob *jobs, int kChunk, int win_diags)
 {
     constexpr int T = K * (K + 1) / 2;
     constexpr int NH = K + 1;                  // deepest diagonal a candidate reaches back to
@@ -677,6 +679,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     uint8_t *bpo1 = bpo0 + kChunk * 32;
     double *cso0 = reinterpret_cast<double *>(bpo1 + kChunk * 32);      // 8-byte aligned: every block above is a multiple of 8 bytes
     double *cso1 = cso0 + kChunk * 32;
+    int *bos = reinterpret_cast<int *>(cso1 + kChunk * 32);       // band offsets of diagonals start-NH .. start+kChunk-1
     const double pen = *job.del_penalty;
     const float *g_costs = job.costs;
     const int32_t *g_ypath = job.ypath;
@@ -686,12 +689,19 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
     // chunk c = node diagonals [c*kChunk, (c+1)*kChunk); its cost diagonals (aa - 2) are one contiguous,
     // 16-byte aligned run in HBM (kChunk is even and so is the band width, so kChunk*tb and 2*tb floats are
     // multiples of 4): read as float4, stored as fp64 (the recurrence adds them to fp64 cumulative costs).
-    auto stage = [&](int c, int first_thread, int nthreads) {
+    // `sync` orders the two passes among the calling threads: band offsets of the chunk (+ NH diagonals of
+    // history) go to shared memory first, so that every later value is computed from shared memory instead of
+    // dependent global loads (the staging warps used to be as busy as the recurrence warp)
+    auto stage = [&](int c, int first_thread, int nthreads, auto sync) {
         const int start = c * kChunk;
         double *cb = (c & 1) ? cbuf1 : cbuf0;
         double *ov = (c & 1) ? ov1 : ov0;
         int *dl = (c & 1) ? dl1 : dl0;
         uint8_t *oc = (c & 1) ? oc1 : oc0;
+        for (int i = first_thread; i < kChunk + NH; i += nthreads) {
+            const int aa = start - NH + i;                      // diagonals before the first one: offset 0
+            bos[i] = (aa >= 0 && aa < nodes_a) ? svx_boff_out(g_ypath, aa, w) : 0;
+        }
         const int lo = start - 2, hi = min(start + kChunk, nodes_a) - 2;   // cost diagonals [lo, hi)
         const int clo = max(lo, 0), chi = min(hi, A);
         if (chi > clo) {
@@ -706,12 +716,13 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             }
             for (int i = 4 * n4 + first_thread; i < n; i += nthreads) dst[i] = (double)__ldg(src + i);
         }
+        sync();
         for (int idx = first_thread; idx < kChunk * 32; idx += nthreads) {
             const int i = idx >> 5, l = idx & 31, aa = start + i;
             int code = SVX_BP_NONE;
             double val = INFINITY;
             if (aa < nodes_a && l < B) {
-                const int yy = l + svx_boff_out(g_ypath, aa, w), xx = aa - yy;
+                const int yy = l + bos[NH + i], xx = aa - yy;
                 // every type ending here reads cost cell (xx-1, yy-1): it must exist (also for the deletions -
                 // reference quirk, dp_core.pyx:382,390; its anti-diagonal aa - 2 < A always holds for aa <= A + 1)
                 if ((unsigned)(xx - 1) < (unsigned)s0 && (unsigned)(yy - 1) < (unsigned)s1) code = kNoOvr;
@@ -726,8 +737,7 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
             const int back = sft == 0 ? 1 : sft;
             int d = 0;
             if (aa < nodes_a && sft != 1) {
-                // diagonals before the first one count as offset 0 (they only ever hold +inf)
-                d = svx_boff_out(g_ypath, aa, w) - (aa - back >= 0 ? svx_boff_out(g_ypath, aa - back, w) : 0);
+                d = bos[NH + i] - bos[NH + i - back];
                 if (sft) d = min(max(d, -K), NH) * 8;       // inside the ring row's padding whatever the path does
             }
             dl[idx] = d;
@@ -736,16 +746,17 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 
     auto flush = [&](int c, int first_thread, int nthreads) {
         const int start = c * kChunk;
-        const int n = min(kChunk, nodes_a - start) * B;
+        const int nrows = min(kChunk, nodes_a - start);
         const double *cso = (c & 1) ? cso1 : cso0;
         const uint8_t *bpo = (c & 1) ? bpo1 : bpo0;
         double *gc = g_csum + (size_t)start * B;
         uint8_t *gb = g_bp + (size_t)start * B;
-        for (int idx = first_thread; idx < n; idx += nthreads) {
-            const int i = idx / B, b = idx - i * B;
-            gc[idx] = cso[i * 32 + b];
-            gb[idx] = bpo[i * 32 + b];
-        }
+        const int l = first_thread & 31;
+        if (l < B)
+            for (int i = first_thread >> 5; i < nrows; i += nthreads >> 5) {      // a warp per row, a lane per slot
+                gc[i * B + l] = cso[i * 32 + l];
+                gb[i * B + l] = bpo[i * 32 + l];
+            }
     };
 
     // ---- phase 1 ------------------------------------------------------------------------------
@@ -796,13 +807,14 @@ __global__ void __launch_bounds__(128) k_banded_dp_tri(const SvxBandJob *jobs, i
 #ifdef SVX_DP_TIMING
     long long tm0 = clock64(), tm1 = 0, tm2 = 0;
 #endif
-    stage(0, tid, blockDim.x);
+    stage(0, tid, blockDim.x, [] { __syncthreads(); });
     __syncthreads();
+    auto stagers_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kDpThreads - 32) : "memory"); };
     double prev = INFINITY, prev2 = INFINITY;     // csum of the previous two diagonals, this lane
     for (int c = 0; c < nchunks; ++c) {
         if (warp != 0) {
-            if (c >= 1) flush(c - 1, tid - 32, blockDim.x - 32);
-            if (c + 1 < nchunks) stage(c + 1, tid - 32, blockDim.x - 32);
+            if (c >= 1) flush(c - 1, tid - 32, kDpThreads - 32);
+            if (c + 1 < nchunks) stage(c + 1, tid - 32, kDpThreads - 32, stagers_sync);
         } else {
             const double *cb = (c & 1) ? cbuf1 : cbuf0;
             const double *ov = ((c & 1) ? ov1 : ov0) + lane;
@@ -1173,7 +1185,7 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
     if (chunk < STEP) chunk = STEP;
     const size_t dp_bytes = (size_t)2 * (chunk * tb + 32) * sizeof(double) + (size_t)2 * chunk * 32 * sizeof(double) +
                             (size_t)NH * RS * sizeof(double) + (size_t)2 * chunk * (NH + 1) * sizeof(int) + (size_t)2 * chunk * 32 +
-                            (size_t)2 * chunk * 32 + (size_t)2 * chunk * 32 * sizeof(double) + 16;
+                            (size_t)2 * chunk * 32 + (size_t)2 * chunk * 32 * sizeof(double) + (size_t)(chunk + NH) * sizeof(int) + 16;
     if (dp_bytes > 220 * 1024) return -1;
     // walk window: whole job when it fits in ~96 KB, otherwise 96 KB windows
     const int per_diag = bmax + (int)sizeof(int);
@@ -1185,7 +1197,7 @@ static int launch_dp_tri(const SvxBandJob *jobs_d, int njobs, int bmax, int amax
     const size_t smem = dp_bytes > walk_bytes ? dp_bytes : walk_bytes;
     auto kern = k_banded_dp_tri<K>;
     if (smem > 40 * 1024) SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<njobs, 128, smem, st>>>(jobs_d, chunk, win);
+    kern<<<njobs, kDpThreads, smem, st>>>(jobs_d, chunk, win);
     SVX_LAUNCH_CHECK();
     return SVX_OK;
 }
