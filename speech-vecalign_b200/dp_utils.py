@@ -16,6 +16,7 @@ order; ``width_over2 < 3`` is raised to 3 (:391-393); torch CUDA inputs are norm
 ``writeback=True`` (the reference's callers never reuse them).
 """
 import logging
+import os
 
 import numpy as np
 import torch
@@ -149,7 +150,8 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
         # ~512 MB of embeddings per chunk (10 ms of PCIe): enough chunks to overlap copy and compute, few
         # enough that per-chunk planning (RNG replay, descriptors) stays off the critical path
         total_bytes = sum(4 * (sh0[0] * sh0[1] + sh1[0] * sh1[1]) * sh0[2] for (sh0, _), (sh1, _) in metas)
-        nchunks = max(1, min(8, P // 4, int(total_bytes // (512 << 20))))
+        cap = int(os.environ.get("SVX_PIPE_CHUNKS", "8"))
+        nchunks = max(1, min(cap, P // 4, int(total_bytes * cap // (4096 << 20))))
     bounds = [P * i // nchunks for i in range(nchunks + 1)]
     cur = torch.cuda.current_stream(dev)
     piped = nchunks > 1
