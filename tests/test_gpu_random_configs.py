@@ -40,7 +40,7 @@ _bin_events = []
 # soak runs: SVX_FUZZ_CASES=400 SVX_FUZZ_SEED=99 python -m pytest tests/test_gpu_random_configs.py
 _N_CASES = int(os.environ.get("SVX_FUZZ_CASES", "36"))
 _SEED = int(os.environ.get("SVX_FUZZ_SEED", "2024"))
-_MAX_TIES = max(2, _N_CASES // 15)
+_MAX_TIES = max(4, _N_CASES // 15)
 
 
 def _knob_tie(oracle, r, g, case):
