@@ -4,6 +4,7 @@ keyword arguments, defaults, side effects (``"%s:%s:%.6f"`` lines, vecalign.py:1
 fixes; the numerics run on the GPU through ``dp_utils.vecalign``.
 """
 import logging
+import os
 import math
 import pickle
 import sys
@@ -11,7 +12,8 @@ from pathlib import Path
 from typing import List, Optional, Set, Tuple, Union
 
 from .dp_utils import vecalign
-from .embedding_utils import make_doc_embedding, read_in_embeddings
+from .embedding_utils import (make_doc_embedding, make_doc_embedding_device, read_in_embedding_rows,
+                              read_in_embeddings)
 
 logger = logging.getLogger("vecalign")
 
@@ -88,17 +90,23 @@ def align(src: str, tgt: str, src_embed: List[str], src_stopes: bool, tgt_stopes
              else make_alignment_types(alignment_max_size))
     width_over2 = width_over2_for(src_max, tgt_max, search_buffer_size)
 
-    src_map, src_rows = read_in_embeddings(src_embed[0], src_embed[1], src_stopes, src_fp16)
-    tgt_map, tgt_rows = read_in_embeddings(tgt_embed[0], tgt_embed[1], tgt_stopes, tgt_fp16)
     logger.info(f'Aligning src={src} to tgt={tgt}')
     src_lines = open(src, 'rt', encoding="utf-8").readlines()
     tgt_lines = open(tgt, 'rt', encoding="utf-8").readlines()
-    vecs0 = make_doc_embedding(src_map, src_rows, src_lines, src_max,
-                               ignore_indices=load_ignore_index_file(src_ignore_indices) if src_ignore_indices else None,
-                               overlap_segments=overlap_segments)
-    vecs1 = make_doc_embedding(tgt_map, tgt_rows, tgt_lines, tgt_max,
-                               ignore_indices=load_ignore_index_file(tgt_ignore_indices) if tgt_ignore_indices else None,
-                               overlap_segments=overlap_segments)
+    src_ign = load_ignore_index_file(src_ignore_indices) if src_ignore_indices else None
+    tgt_ign = load_ignore_index_file(tgt_ignore_indices) if tgt_ignore_indices else None
+    if debug_save_stack or os.environ.get("SVX_HOST_GATHER"):
+        # the reference's host path (embedding_utils.py:135-203): the pickled stack then holds host arrays
+        src_map, src_rows = read_in_embeddings(src_embed[0], src_embed[1], src_stopes, src_fp16)
+        tgt_map, tgt_rows = read_in_embeddings(tgt_embed[0], tgt_embed[1], tgt_stopes, tgt_fp16)
+        vecs0 = make_doc_embedding(src_map, src_rows, src_lines, src_max, ignore_indices=src_ign, overlap_segments=overlap_segments)
+        vecs1 = make_doc_embedding(tgt_map, tgt_rows, tgt_lines, tgt_max, ignore_indices=tgt_ign, overlap_segments=overlap_segments)
+    else:
+        # same tensors, bit for bit, gathered on the GPU from the rows in their on-disk dtype (svx_gather_doc_embedding)
+        src_map, src_rows = read_in_embedding_rows(src_embed[0], src_embed[1], src_stopes, src_fp16)
+        tgt_map, tgt_rows = read_in_embedding_rows(tgt_embed[0], tgt_embed[1], tgt_stopes, tgt_fp16)
+        vecs0 = make_doc_embedding_device(src_map, src_rows, src_lines, src_max, ignore_indices=src_ign, overlap_segments=overlap_segments)
+        vecs1 = make_doc_embedding_device(tgt_map, tgt_rows, tgt_lines, tgt_max, ignore_indices=tgt_ign, overlap_segments=overlap_segments)
 
     stack = vecalign(vecs0=vecs0, vecs1=vecs1, final_alignment_types=types,
                      del_percentile_frac=del_percentile_frac, width_over2=width_over2,
