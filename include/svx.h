@@ -286,6 +286,11 @@ SVX_API int svx_host_randint_seeded(int nstreams, const uint32_t *seeds, const i
  * For the few-MB descriptor block of a batch.  Both pointers 16-byte aligned. */
 SVX_API int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long long nbytes, void *stream);
 
+/* Host memcpy on `nthreads` threads (page-aligned slices).  Pageable numpy inputs - what the reference's callers
+ * hand to dp_utils.vecalign (dp_utils.py:381) - are staged through pinned buffers with it: one thread of the
+ * driver's own pageable path reaches ~10 GB/s, the PCIe link takes 55. */
+SVX_API int svx_host_memcpy(void *dst, const void *src, long long nbytes, int nthreads);
+
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);

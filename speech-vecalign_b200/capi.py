@@ -99,6 +99,7 @@ def lib():
         "svx_banded_dp": [vp, vp, ci, vp],
         "svx_host_banded_dp": [vp],
         "svx_upload_pinned": [vp, vp, ctypes.c_longlong, vp],
+        "svx_host_memcpy": [vp, vp, ctypes.c_longlong, ci],
         "svx_host_randint_stream": [vp, vp, ci, vp, vp, vp],
         "svx_host_randint_seeded": [ci, vp, vp, vp, vp, vp, ci],
         "svx_host_dense_dp": [vp],
@@ -125,7 +126,7 @@ EXPORTED_SYMBOLS = [
     "svx_normalize_rows", "svx_downsample", "svx_sample_norms", "svx_level_prologue", "svx_gather_doc_embedding", "svx_score_pairs", "svx_del_knob",
     "svx_host_del_knob", "svx_dense_costs", "svx_dense_dp", "svx_dense_tmaps_encode", "svx_path_len", "svx_banded_costs",
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_host_randint_stream",
-    "svx_host_randint_seeded", "svx_upload_pinned", "svx_version",
+    "svx_host_randint_seeded", "svx_upload_pinned", "svx_host_memcpy", "svx_version",
     "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
 ]
 

@@ -152,3 +152,27 @@ extern "C" int svx_host_randint_seeded(int nstreams, const uint32_t *seeds, cons
     for (auto &th : pool) th.join();
     return SVX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Parallel host memcpy (pageable -> pinned staging of host inputs).
+// ---------------------------------------------------------------------------------------------
+#include <string.h>
+extern "C" int svx_host_memcpy(void *dst, const void *src, long long nbytes, int nthreads)
+{
+    if (nbytes <= 0) return SVX_OK;
+    if (!dst || !src) { svx_set_error("svx_host_memcpy: null pointer"); return SVX_ERR_ARG; }
+    if (nthreads < 1) nthreads = 1;
+    const long long min_slice = 1 << 20;
+    if ((long long)nthreads * min_slice > nbytes) nthreads = (int)((nbytes + min_slice - 1) / min_slice);
+    if (nthreads <= 1) { memcpy(dst, src, (size_t)nbytes); return SVX_OK; }
+    const long long slice = ((nbytes + nthreads - 1) / nthreads + 4095) & ~4095LL;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        const long long lo = (long long)t * slice;
+        if (lo >= nbytes) break;
+        const long long n = nbytes - lo < slice ? nbytes - lo : slice;
+        pool.emplace_back([=] { memcpy((char *)dst + lo, (const char *)src + lo, (size_t)n); });
+    }
+    for (auto &th : pool) th.join();
+    return SVX_OK;
+}

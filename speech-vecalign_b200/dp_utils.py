@@ -47,6 +47,55 @@ def _side_stream(dev, name):
     return _SIDE_STREAMS[key]
 
 
+# Pageable host inputs (plain numpy arrays - what the reference's callers pass, dp_utils.py:381) go through a
+# ring of pinned staging slots: a multi-threaded memcpy into a slot (svx_host_memcpy), then an asynchronous copy
+# from it.  The driver's own pageable path is a single staging thread (~10 GB/s measured; the link takes 55).
+_STAGE_SLOT = 64 << 20
+_STAGE = {"slots": [], "events": [], "next": 0}
+_STAGE_MIN = 4 << 20                      # smaller arrays are not worth a slot round trip
+
+
+def _stage_threads():
+    try:
+        return max(1, min(16, len(os.sched_getaffinity(0))))
+    except Exception:
+        return max(1, min(16, os.cpu_count() or 1))
+
+
+def _stage_slot():
+    """Next pinned slot of the ring, free again (its last device copy has completed)."""
+    nslots = int(os.environ.get("SVX_STAGE_SLOTS", "8"))
+    st = _STAGE
+    if len(st["slots"]) < nslots:
+        st["slots"].append(torch.empty(_STAGE_SLOT, dtype=torch.uint8, pin_memory=True))
+        st["events"].append(None)
+        i = len(st["slots"]) - 1
+    else:
+        i = st["next"] % nslots
+        if st["events"][i] is not None:
+            st["events"][i].synchronize()
+    st["next"] = i + 1
+    return i
+
+
+def _staged_copy(src_ptr, nbytes, dst):
+    """pageable host memory [src_ptr, +nbytes) -> device tensor dst (contiguous), on the current stream."""
+    flat = dst.view(torch.uint8).view(-1)
+    nthreads = _stage_threads()
+    stream = torch.cuda.current_stream(dst.device)
+    off = 0
+    while off < nbytes:
+        n = min(_STAGE_SLOT, nbytes - off)
+        i = _stage_slot()
+        slot = _STAGE["slots"][i]
+        capi.check(capi.lib().svx_host_memcpy(slot.data_ptr(), src_ptr + off, n, nthreads), "svx_host_memcpy")
+        flat[off:off + n].copy_(slot[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        _STAGE["events"][i] = ev
+        off += n
+
+
 def _to_device(v, dev):
     """(K, N, D) on the device, fp32 or — an extension for embeddings kept in their on-disk dtype — fp16
     (widened on the device by _widen).  Returns (tensor, host_array_or_None)."""
@@ -57,12 +106,22 @@ def _to_device(v, dev):
             if not v.is_contiguous():
                 raise ValueError("device tensors must be contiguous")
             return v, None
-        return v.contiguous().to(dev, non_blocking=True), None
+        v = v.contiguous()
+        nbytes = v.numel() * v.element_size()
+        if v.is_pinned() or nbytes < _STAGE_MIN:
+            return v.to(dev, non_blocking=True), None
+        t = torch.empty(v.shape, dtype=v.dtype, device=dev)
+        _staged_copy(v.data_ptr(), nbytes, t)
+        return t, None
     v = np.asarray(v)
     if v.dtype not in (np.float32, np.float16) or v.ndim != 3:
         # the reference's Cython buffers reject anything else (dp_core.pyx:168-171)
         raise ValueError("Buffer dtype mismatch, expected 'float' with ndim=3")
-    t = torch.from_numpy(np.ascontiguousarray(v)).to(dev, non_blocking=True)
+    c = np.ascontiguousarray(v)
+    if c.nbytes < _STAGE_MIN:
+        return torch.from_numpy(c).to(dev, non_blocking=True), v
+    t = torch.empty(c.shape, dtype=torch.float32 if c.dtype == np.float32 else torch.float16, device=dev)
+    _staged_copy(c.ctypes.data, c.nbytes, t)
     return t, v
 
 

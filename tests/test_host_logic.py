@@ -295,3 +295,14 @@ def test_c_randint_replay_equals_numpy(svb):
         assert np.array_equal(np.random.randint(0, int(h), int(c)), o)
     st2 = np.random.get_state()
     assert np.array_equal(st2[1], key) and st2[2] == pos[0]
+
+
+@pytest.mark.parametrize("nbytes,nthreads", [(0, 4), (1, 4), (4095, 2), (1 << 20, 1), (5_000_003, 3), (37_000_001, 8), (37_000_001, 64)])
+def test_host_memcpy_threads(svb, nbytes, nthreads):
+    """svx_host_memcpy (pinned staging of pageable inputs): byte-exact for any size / thread count."""
+    rng = np.random.default_rng(nbytes % 97)
+    src = rng.integers(0, 256, size=nbytes + 64, dtype=np.uint8)
+    dst = np.zeros(nbytes + 64, dtype=np.uint8)
+    assert svb.capi.lib().svx_host_memcpy(dst.ctypes.data + 32, src.ctypes.data + 32, nbytes, nthreads) == 0
+    assert np.array_equal(dst[32:32 + nbytes], src[32:32 + nbytes])
+    assert not dst[:32].any() and not dst[32 + nbytes:].any()
