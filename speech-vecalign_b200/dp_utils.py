@@ -56,6 +56,8 @@ _STAGE_MIN = 4 << 20                      # smaller arrays are not worth a slot 
 
 
 def _stage_threads():
+    if os.environ.get("SVX_STAGE_THREADS"):
+        return max(1, int(os.environ["SVX_STAGE_THREADS"]))
     try:
         return max(1, min(16, len(os.sched_getaffinity(0))))
     except Exception:
