@@ -138,12 +138,28 @@ __global__ void __launch_bounds__(256) k_dense_dp(const SvxDenseJob *jobs)
     const int L = sp + 1;
     const float penf = (float)(*job.del_penalty);
     const int ld = s1 + 1;
+    // The cost of a thread's cell on diagonal k + 1 is requested BEFORE the barrier that ends diagonal k (the
+    // loads of one anti-diagonal are s1-1 floats apart: one L2 sector each, ~500 cycles that every warp then
+    // waited for at the next barrier).  volatile asm: ptxas otherwise sinks the load to its use.
+    const float *costs = job.costs;
+    auto cost_prefetch = [&](int k, int p) -> float {
+        const int q = k - p;
+        const int r = swap ? q : p, c = swap ? p : q;
+        float v = 0.0f;
+        if (p <= sp && q >= 0 && q <= sq && r > 0 && c > 0)
+            asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(costs + (size_t)(r - 1) * s1 + (c - 1)));
+        return v;
+    };
+    const bool single = L <= (int)blockDim.x;          // one cell per thread and diagonal
+    float cnext = single ? cost_prefetch(0, (int)threadIdx.x) : 0.0f;
     for (int k = 0; k <= s0 + s1; ++k) {
         double *cur = diag + (k % 3) * L;
         const double *d1 = diag + ((k + 2) % 3) * L;   // diagonal k-1
         const double *d2 = diag + ((k + 1) % 3) * L;   // diagonal k-2
         const int plo = k - sq > 0 ? k - sq : 0;
         const int phi = k < sp ? k : sp;
+        const float cthis = cnext;
+        if (single) cnext = cost_prefetch(k + 1, (k + 1 - sq > 0 ? k + 1 - sq : 0) + (int)threadIdx.x);   // p of this thread's cell on k + 1
         for (int p = plo + (int)threadIdx.x; p <= phi; p += blockDim.x) {
             const int q = k - p;
             const int r = swap ? q : p, c = swap ? p : q;
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(256) k_dense_dp(const SvxDenseJob *jobs)
                 const double dg = d2[p - 1];
                 const double left = swap ? d1[p - 1] : d1[p];   // csum[r, c-1]
                 const double up = swap ? d1[p] : d1[p - 1];     // csum[r-1, c]
-                val = svx_dense_cell(dg, left, up, job.costs[(size_t)(r - 1) * s1 + (c - 1)], penf, &bp);
+                val = svx_dense_cell(dg, left, up, single ? cthis : costs[(size_t)(r - 1) * s1 + (c - 1)], penf, &bp);
             }
             cur[p] = val;
             job.bp[(size_t)r * ld + c] = (uint8_t)bp;
