@@ -291,11 +291,91 @@ SVX_API int svx_upload_pinned(void *dst_d, const void *src_pinned_h, long long n
  * driver's own pageable path reaches ~10 GB/s, the PCIe link takes 55. */
 SVX_API int svx_host_memcpy(void *dst, const void *src, long long nbytes, int nthreads);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole path: one batch of document pairs from overlap tensors to alignment records.
+ * Replaces the control flow of dp_utils.vecalign (dp_utils.py:381-537) - level sizes (:403-408), the
+ * sampling plan and RNG call order (:288-302, :339-346, :423-455), the coarse-to-fine loop (:457-535) -
+ * for MANY pairs per call.  The caller owns two buffers, sized by svx_workspace_bytes / svx_plan_info:
+ * the device ARENA (every intermediate and the results) and a host STAGING block (descriptors + RNG
+ * draws; pinned memory lets the upload bypass the DMA queue).  A plan can be re-bound and re-run.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct SvxAlignParams {
+    int32_t k0, k1, dim;           /* overlaps per side, embedding dimension (vecs are (k, n, dim) fp32)     */
+    int32_t ntypes;                /* final_alignment_types (vecalign.py:154-171), reference order           */
+    int8_t xo[SVX_MAX_TYPES], yo[SVX_MAX_TYPES];
+    double del_percentile_frac;
+    int32_t width_over2;           /* raised to 3 like dp_utils.py:391-393                                   */
+    int32_t max_size_full_dp, costs_sample_size, num_samps_for_norm;
+    int32_t cost_mode;             /* SVX_COST_*                                                             */
+    int32_t keep_all;              /* 1: keep every overlap of every level + the dense csum (parity/debug)   */
+    int32_t unfused_prologue;      /* 1: the three separate prologue launchers (A/B)                         */
+    int32_t skip_norms0, skip_norms1; /* 1: the caller writes level-0 norms itself (norms0= / norms1=, dp_utils.py:428-444) */
+} SvxAlignParams;
+
+typedef struct SvxPlan SvxPlan;    /* opaque */
+
+typedef struct SvxPlanInfo {
+    int32_t npairs, nrecords;      /* records = (pair, level) */
+    int32_t max_depth, band, width_over2, per0, per1, fused_prologue, nlaunchers;
+    int64_t ndraw_calls;
+    int64_t arena_bytes;           /* device workspace                                          */
+    int64_t host_bytes;            /* staging block = the host-initialised prefix of the arena  */
+    int64_t result_offset;         /* [result_offset, arena_bytes): records, counts, status     */
+    double fallback_del_penalty;   /* dp_utils.py:315-321                                       */
+} SvxPlanInfo;
+
+/* per-record byte offsets into the arena (svx_plan_array(SVX_PA_OFFSETS + key)) */
+enum {
+    SVX_PO_IDX0, SVX_PO_IDX1, SVX_PO_XI, SVX_PO_YI, SVX_PO_DELPEN, SVX_PO_TMAPS,
+    SVX_PO_NORMS0, SVX_PO_NORMS1, SVX_PO_VEC0, SVX_PO_VEC1, SVX_PO_MEAN0, SVX_PO_MEAN1, SVX_PO_MBAR0, SVX_PO_MBAR1,
+    SVX_PO_SCORES, SVX_PO_PERM, SVX_PO_DCOST, SVX_PO_DDOTS, SVX_PO_DBP, SVX_PO_DCSUM, SVX_PO_YPATH, SVX_PO_BCOST,
+    SVX_PO_BBP, SVX_PO_BCSUM, SVX_PO_RECS, SVX_PO_NRECS, SVX_PO_STATUS, SVX_PO_COUNT
+};
+/* int64 arrays of a plan: per pair (FIRST, NLEV, DEPTH, TOP_REC, TGT_REC), per record, per RNG call */
+enum {
+    SVX_PA_FIRST, SVX_PA_NLEV, SVX_PA_DEPTH, SVX_PA_REC_PAIR, SVX_PA_REC_LEVEL, SVX_PA_RS0, SVX_PA_RS1, SVX_PA_A, SVX_PA_T,
+    SVX_PA_BANDED, SVX_PA_REC_CAP, SVX_PA_NSAMP, SVX_PA_HAS_DRAW, SVX_PA_TOP_REC, SVX_PA_TGT_REC,
+    SVX_PA_DRAW_PAIR, SVX_PA_DRAW_HIGH, SVX_PA_DRAW_COUNT, SVX_PA_DRAW_OFF, SVX_PA_DRAW_BEGIN,
+    SVX_PA_OFFSETS = 64
+};
+
+SVX_API int svx_plan_create(const SvxAlignParams *params, int npairs, const int32_t *n0, const int32_t *n1, SvxPlan **out);
+SVX_API void svx_plan_destroy(SvxPlan *plan);
+SVX_API int svx_plan_info(const SvxPlan *plan, SvxPlanInfo *info);
+SVX_API int svx_plan_array(const SvxPlan *plan, int which, const int64_t **ptr, int64_t *count);   /* borrowed */
+/* Writes default penalties, TMA descriptors and every job descriptor for (arena_d, v0_d[p], v1_d[p]) into stage_h. */
+SVX_API int svx_plan_bind(SvxPlan *plan, void *arena_d, void *stage_h, const void *const *v0_d, const void *const *v1_d);
+/* The reference's np.random draws (np.random.choice(range(n), size=k), dp_utils.py:301-302,346) written into the
+ * staging block in the reference's call order: one np.random.seed(seeds[p]) stream per pair, or the caller's global
+ * stream continued from np.random.get_state() (key, pos) and handed back for set_state. */
+SVX_API int svx_plan_draw_seeded(SvxPlan *plan, const uint32_t *seeds, int nthreads);
+SVX_API int svx_plan_draw_stream(SvxPlan *plan, uint32_t *key624, int32_t *pos);
+/* staging block -> arena; norms preset to 1.0 (dp_utils.py:356-357), counts and status cleared.  Asynchronous. */
+SVX_API int svx_plan_upload(SvxPlan *plan, int stage_is_pinned, void *stream);
+SVX_API int svx_plan_launcher_name(const SvxPlan *plan, int launcher, char *buf, int cap);
+/* Enqueues launcher `launcher` (-1: the whole chain, in order) for pairs [pair_lo, pair_hi).  Asynchronous. */
+SVX_API int svx_plan_enqueue(const SvxPlan *plan, int launcher, int pair_lo, int pair_hi, void *stream);
+/* Level-0 alignment records in document order, level-0 deletion penalty and the OR of all status words of every
+ * pair, copied to host arrays; pair p owns recs_out[rec_begin[p], rec_begin[p+1]).  Synchronises the stream. */
+SVX_API int svx_plan_fetch(const SvxPlan *plan, SvxAlignRec *recs_out, const int64_t *rec_begin, int32_t *nrecs_out,
+                           double *del_penalty_out, int32_t *status_out, void *stream);
+
+/* The two calls of a host without a planner of its own: size the buffers, then align a batch (plan, seeded draws,
+ * upload, launch chain, fetch; synchronous).  v0_d[p] / v1_d[p]: device (k, n[p], dim) fp32, normalised in place
+ * like dp_utils.py:396-397. */
+SVX_API int svx_workspace_bytes(const SvxAlignParams *params, int npairs, const int32_t *n0, const int32_t *n1,
+                                int64_t *arena_bytes, int64_t *stage_bytes);
+SVX_API int svx_align_batch(const SvxAlignParams *params, int npairs, const int32_t *n0, const int32_t *n1,
+                            const void *const *v0_d, const void *const *v1_d, const uint32_t *seeds,
+                            void *arena_d, int64_t arena_bytes, void *stage_h, int64_t stage_bytes, int stage_is_pinned,
+                            SvxAlignRec *recs_out, const int64_t *rec_begin, int32_t *nrecs_out, double *del_penalty_out,
+                            int32_t *status_out, void *stream);
+
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);
 SVX_API long long svx_launch_count(int reset); /* kernels launched since the last reset */
-SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec,7 Level,8 Gather */
+SVX_API int svx_sizeof_job(int which); /* 0 Rows,1 Down,2 Norm,3 Score,4 Dense,5 Band,6 AlignRec,7 Level,8 Gather,9 AlignParams,10 PlanInfo */
 
 #ifdef __cplusplus
 }

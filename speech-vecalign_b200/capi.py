@@ -52,7 +52,18 @@ BAND = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("ypath", _P), 
                  ("xo", np.int8, (SVX_MAX_TYPES,)), ("yo", np.int8, (SVX_MAX_TYPES,)),
                  ("amax", np.int16)], align=True)
 
-_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER]
+PARAMS = np.dtype([("k0", np.int32), ("k1", np.int32), ("dim", np.int32), ("ntypes", np.int32),
+                   ("xo", np.int8, (SVX_MAX_TYPES,)), ("yo", np.int8, (SVX_MAX_TYPES,)),
+                   ("del_percentile_frac", np.float64),
+                   ("width_over2", np.int32), ("max_size_full_dp", np.int32), ("costs_sample_size", np.int32),
+                   ("num_samps_for_norm", np.int32), ("cost_mode", np.int32), ("keep_all", np.int32),
+                   ("unfused_prologue", np.int32), ("skip_norms0", np.int32), ("skip_norms1", np.int32)], align=True)
+PLAN_INFO = np.dtype([("npairs", np.int32), ("nrecords", np.int32), ("max_depth", np.int32), ("band", np.int32),
+                      ("width_over2", np.int32), ("per0", np.int32), ("per1", np.int32), ("fused_prologue", np.int32),
+                      ("nlaunchers", np.int32), ("ndraw_calls", np.int64), ("arena_bytes", np.int64), ("host_bytes", np.int64),
+                      ("result_offset", np.int64), ("fallback_del_penalty", np.float64)], align=True)
+
+_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER, PARAMS, PLAN_INFO]
 
 _lib = None
 
@@ -105,11 +116,25 @@ def lib():
         "svx_host_dense_dp": [vp],
         "svx_version": [],
         "svx_sizeof_job": [ci],
+        "svx_plan_create": [vp, ci, vp, vp, vp],
+        "svx_plan_info": [vp, vp],
+        "svx_plan_array": [vp, ci, vp, vp],
+        "svx_plan_bind": [vp, vp, vp, vp, vp],
+        "svx_plan_draw_seeded": [vp, vp, ci],
+        "svx_plan_draw_stream": [vp, vp, vp],
+        "svx_plan_upload": [vp, ci, vp],
+        "svx_plan_launcher_name": [vp, ci, vp, ci],
+        "svx_plan_enqueue": [vp, ci, ci, ci, vp],
+        "svx_plan_fetch": [vp, vp, vp, vp, vp, vp, vp],
+        "svx_workspace_bytes": [vp, ci, vp, vp, vp, vp],
+        "svx_align_batch": [vp, ci, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ci, vp, vp, vp, vp, vp, vp],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = ci
+    L.svx_plan_destroy.argtypes = [vp]
+    L.svx_plan_destroy.restype = None
     L.svx_launch_count.argtypes = [ci]
     L.svx_launch_count.restype = ctypes.c_longlong
     L.svx_last_error_string.argtypes = []
@@ -128,6 +153,9 @@ EXPORTED_SYMBOLS = [
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_host_randint_stream",
     "svx_host_randint_seeded", "svx_upload_pinned", "svx_host_memcpy", "svx_version",
     "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
+    "svx_plan_create", "svx_plan_destroy", "svx_plan_info", "svx_plan_array", "svx_plan_bind", "svx_plan_draw_seeded",
+    "svx_plan_draw_stream", "svx_plan_upload", "svx_plan_launcher_name", "svx_plan_enqueue", "svx_plan_fetch",
+    "svx_workspace_bytes", "svx_align_batch",
 ]
 
 

@@ -4,11 +4,13 @@
 //   svx_banded_dp    (dp_core.pyx:269-404 sparse_dp; dp_utils.py:89-143 sparse_traceback +
 //                     process_scores; dp_utils.py:177-275 path glue)
 #include <stdlib.h>
+#include <string.h>
 #include <stdio.h>
 #include <type_traits>
 #include <utility>
 #include "svx_common.cuh"
 #include "svx_dp.h"
+#include "svx_banded_p2.h"
 
 namespace {
 
@@ -110,8 +112,28 @@ k_banded_costs(const SvxBandJob *jobs, int dim, int ta, int lb)
             const float *gv0 = job.v0, *gv1 = job.v1;
             // slice `sl` -> buffer sl & 1, 16 bytes per cp.async, zero-filled (src-size 0) for rows outside
             // the documents / overlaps
+            const bool many_items = nitems > kMaxItems * (int)blockDim.x;     // very wide bands: sources resolved per copy
             auto issue = [&](int sl) {
                 const unsigned buf = tile_u32 + (unsigned)((sl & 1) * buf_floats * (int)sizeof(float));
+                if (many_items) {
+                    for (int f = tid; f < nitems; f += (int)blockDim.x) {
+                        const int row = f / (kBC / 4), c4 = f % (kBC / 4);
+                        const float *gp = gv0;
+                        int nbytes = 0;
+                        if (row < xrows) {
+                            const int k = kx0 + row / NX, seg = xlo + row % NX;
+                            if (k < job.k0 && seg >= 0 && seg < s0) { gp = gv0 + ((size_t)k * s0 + seg) * dim + 4 * c4 + sl * kBC; nbytes = 16; }
+                        } else {
+                            const int r2 = row - xrows;
+                            const int k = ky0 + r2 / NY, seg = ylo + r2 % NY;
+                            if (k < job.k1 && seg >= 0 && seg < s1) { gp = gv1 + ((size_t)k * s1 + seg) * dim + 4 * c4 + sl * kBC; nbytes = 16; }
+                        }
+                        const unsigned dst = buf + (unsigned)(((f >> 3) * kBS + 4 * (f & 7)) * (int)sizeof(float));
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gp), "r"(nbytes));
+                    }
+                    asm volatile("cp.async.commit_group;\n" ::);
+                    return;
+                }
 #pragma unroll
                 for (int it = 0; it < kMaxItems; ++it) {
                     const int f = tid + it * (int)blockDim.x;
@@ -1070,7 +1092,8 @@ int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int d
     // to move the tile's rows in kMaxItems (8) pieces each
     auto threads_for = [&](int t) {
         const size_t items = (size_t)maxk * (t + 2 * band - 1) * (kBC / 4);
-        const int need = (int)(((items + 7) / 8 + 31) & ~(size_t)31);
+        int need = (int)(((items + 7) / 8 + 31) & ~(size_t)31);
+        if (need > 384) need = 384;          // wider: the kernel resolves the copy sources per slice (many_items)
         return need > t * lb ? need : t * lb;
     };
     auto fits = [&](int t) {
@@ -1078,6 +1101,7 @@ int launch_costs(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int d
                threads_for(t) <= 384;
     };
     if (!fits(ta) && ta > 16) ta = 16;
+    while (ta > 1 && (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float) > 220 * 1024) --ta;   // very wide bands
     const int threads = threads_for(ta);
     if (threads > 384) return -1;
     const size_t smem = (size_t)2 * maxk * (ta + 2 * band - 1) * kBS * sizeof(float);   // two slice buffers
@@ -1134,11 +1158,20 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
     for (int jb0 = 0; jb0 < njobs; jb0 += SVX_MAX_GRID_Y) {
         const int nj = njobs - jb0 < SVX_MAX_GRID_Y ? njobs - jb0 : SVX_MAX_GRID_Y;
         int rc = -1;
-        // SVX_COSTS_CELL=1 selects the thread-per-cell kernel also for K <= 5 (A/B measurements)
-        static const bool per_cell = getenv("SVX_COSTS_CELL") && atoi(getenv("SVX_COSTS_CELL")) != 0;
-        // measured on B200: the register-blocked kernel wins for K <= 4 (cfg2: 18.1 -> 16.1 ms, coarse levels
-        // 3.6 -> 1.8 ms); at K = 5 (15 types, 60 accumulators per thread) the thread-per-cell kernel is faster
-        if (standard && !per_cell && K <= 4 && (j0.band & 1) == 0) {
+        // A/B switches (read once): SVX_COSTS_KERNEL = p2 (default: packed FFMA2 blocks, banded_p2.cu) | blk (scalar
+        // 2x2 blocks, K <= 4) | cell (thread per cell); SVX_COSTS_CELL=1 is the older spelling of `cell`
+        static const char *which = getenv("SVX_COSTS_KERNEL") ? getenv("SVX_COSTS_KERNEL") : "p2";
+        static const bool per_cell = (getenv("SVX_COSTS_CELL") && atoi(getenv("SVX_COSTS_CELL")) != 0) || !strcmp(which, "cell");
+        static const bool use_p2 = !per_cell && !strcmp(which, "p2");
+        static const int p2_bc = getenv("SVX_P2_BC") ? atoi(getenv("SVX_P2_BC")) : 16;
+        static const int p2_stages = getenv("SVX_P2_STAGES") ? atoi(getenv("SVX_P2_STAGES")) : 4;
+        static const int p2_prod = getenv("SVX_P2_PRODUCERS") ? atoi(getenv("SVX_P2_PRODUCERS")) : 2;
+        static const int p2_mink = getenv("SVX_P2_MINK") ? atoi(getenv("SVX_P2_MINK")) : 2;   // K = 1 (coarse levels, one type) is copy-bound
+        if (standard && use_p2 && K >= p2_mink && K <= 7)
+            rc = svx_launch_costs_p2(K, jobs_d + jb0, nj, max_alen, j0.band, dim, mode, p2_bc, p2_stages, p2_prod, st);
+        // the scalar register-blocked kernel (round 1): K <= 4 only - at K = 5 its 60 accumulators per thread made
+        // the thread-per-cell kernel faster
+        if (rc == -1 && standard && !per_cell && K <= 4 && (j0.band & 1) == 0) {
             switch (K) {
 #define CASE(KK) case KK: rc = launch_costs_blk<KK>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st); break;
                 CASE(1) CASE(2) CASE(3) CASE(4)
@@ -1154,7 +1187,11 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
                 default: break;
             }
         }
+        // any type list (vecalign.py:165-171 many-to-one lists, hand-written lists): passes over blocks of 4 x 4, or
+        // for very wide bands 2 x 2 / 1 x 1, (x overlap, y overlap) pairs with a type lookup table
         if (rc == -1) rc = launch_costs<4, 4, false>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st);
+        if (rc == -1) rc = launch_costs<2, 2, false>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st);
+        if (rc == -1) rc = launch_costs<1, 1, false>(jobs_d + jb0, nj, max_alen, j0.band, dim, mode, st);
         SVX_REQUIRE(rc != -1, SVX_ERR_UNSUPPORTED, "svx_banded_costs: band %d too wide for one CTA", j0.band);
         if (rc != SVX_OK) return rc;
     }
@@ -1226,12 +1263,14 @@ extern "C" int svx_banded_dp(const SvxBandJob *jobs_d, const SvxBandJob *jobs_h,
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (standard && bmax + K <= 32) {      // source-lane wrap-around must land on a lane >= band
+        int rc = -1;                        // -1: the chunk plan does not fit shared memory (K = 8 with bands >= 20)
         switch (K) {
-#define CASE(KK) case KK: return launch_dp_tri<KK>(jobs_d, njobs, bmax, alen_max, st);
+#define CASE(KK) case KK: rc = launch_dp_tri<KK>(jobs_d, njobs, bmax, alen_max, st); break;
             CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9)
 #undef CASE
             default: break;
         }
+        if (rc != -1) return rc;            // otherwise the generic kernel below handles the shape
     }
     // any other type list: generic kernel (shared-memory ring, run-time type loop)
     const int R = ring_size(amax);

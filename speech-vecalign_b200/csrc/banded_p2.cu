@@ -1,0 +1,367 @@
+// banded_p2.cu — level-0 banded costs (dp_core.pyx:165-267 make_sparse_costs) for the standard type
+// sets (make_alignment_types, vecalign.py:154-162), register-blocked AND packed: sm_100a's FFMA2.
+//
+// A thread owns a 2 x 2 block of POSITIONS (xx in {2X, 2X+1}, yy in {2Y, 2Y+1}); its cells lie on the
+// anti-diagonals 2e, 2e+1, 2e+1, 2e+2 (e = X + Y is the block-diagonal) and share their operand rows.
+// The two cells that share a y position are one packed fp32x2 accumulator {(2X, y), (2X+1, y)}:
+//
+//     FAST   acc = fma.rn.f32x2(x2, {y, y}, acc)                                   1 FFMA2 per 2 MACs
+//     EXACT  p   = fma.rn.f32x2(x2, {y, y}, {-0.0, -0.0})   == round(x * y)        (the reference's order:
+//            acc = fma.rn.f32x2(p, {1.0, 1.0}, acc)         == round(p + acc)       multiply, THEN add)
+//
+// with x2 = {x[2X][d], x[2X+1][d]}.  -0.0 and 1.0 are kernel ARGUMENTS: ptxas cannot fold them, so the two
+// roundings stay separate (a literal -0.0 / 1.0 is simplified and contracted into one FFMA2, which is not
+// the reference's arithmetic).  x * y + (-0.0) rounds once to round(x * y) with the product's own sign of
+// zero, p * 1.0 + acc is round(p + acc): bit-identical to __fmul_rn + __fadd_rn (tests/test_gpu_functions.py).
+// FFMA2 takes the {y, y} operand as a scalar broadcast (SASS `R.F32`), so no duplication moves are issued,
+// and it occupies the FP32 pipe for two cycles per issue: the exact stream needs 1 issue slot per MAC
+// instead of 2, which is what bounded the scalar kernel (issue-active 82 %, FMA pipe 67 %).
+//
+// Tile = 32 consecutive block-diagonals of one job (65 anti-diagonals, the first and last shared with the
+// neighbouring tiles cell by cell - every band cell belongs to exactly one block, so to exactly one tile).
+// Warp = one band slot (Y - Ymin(e)), lane = block-diagonal: B/2 + 1 warps cover every band cell (proved by
+// enumeration in tests/test_host_logic.py), every lane of every warp owns a block, and the eight lanes of an
+// LDS.128 phase read rows that are equal or consecutive (X and Y advance by 0 or 1 along e): no conflicts.
+// Shared-memory layout of one embedding slice (BC floats): x rows as PAIR ROWS, the two positions of a block
+// interleaved float by float ({x[2X][d], x[2X+1][d]} is then one aligned 8-byte word = one FFMA2 operand),
+// staged with 4-byte cp.async; y rows as [even positions | odd positions], 16-byte cp.async; both through a
+// ring of `nstages` slices with one __syncthreads per slice.
+#include <limits.h>
+#include "svx_common.cuh"
+#include "svx_banded_p2.h"
+
+namespace {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float a, float b)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+template <bool EXACT>
+__device__ __forceinline__ u64 mac2(u64 acc, u64 x2, float y, u64 one2, u64 nz2)
+{
+    const u64 y2 = pack2(y, y);
+    if (EXACT) return fma2(fma2(x2, y2, nz2), one2, acc);
+    return fma2(x2, y2, acc);
+}
+
+constexpr int kNE = 32;                 // block-diagonals per tile = lanes
+
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+// arrives once every cp.async this thread has issued so far has landed (count pre-charged at init: .noinc)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// K: overlaps per side; BC: floats of the embedding dimension per staged slice; DV: floats per operand load.
+// Warps [0, nb) are consumers (nb = band / 2 + 1 band slots), the remaining 1-2 warps are producers: they move
+// slice after slice of the tile's rows into a ring of `nstages` buffers with cp.async and signal each buffer's
+// `full` mbarrier (cp.async.mbarrier.arrive); a consumer warp waits for `full`, multiplies, and arrives on the
+// buffer's `empty` mbarrier.  No CTA-wide barrier in the slice loop: the consumer warps drift apart by up to the
+// ring depth, and the copy address arithmetic stays off the consumers' FP32 pipe (IMAD shares it with FFMA2).
+template <int K, int BC, int DV, bool EXACT>
+__global__ void __launch_bounds__(svx_p2_max_threads(K), 1)
+k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float one, float nz)
+{
+    constexpr int T = K * (K + 1) / 2;
+    constexpr int XS = 2 * BC + 4;      // pair-row stride in floats: 8 consecutive pair rows tile the 32 banks
+    constexpr int YS = BC + 4;
+    static_assert(DV == 2 || DV == 4, "operand loads are 8 or 16 bytes per row");
+    extern __shared__ __align__(16) float tile[];
+    const SvxBandJob &job = jobs[blockIdx.y];
+    const int A = job.a_len;
+    const int e_first = kNE * (int)blockIdx.x - 1;           // e = -1 holds the (odd, odd) cells of diagonal 0
+    const int d_first = max(2 * e_first, 0), d_last = min(2 * (e_first + kNE - 1) + 2, A - 1);
+    if (d_first > d_last) return;
+    const int B = job.band, w = job.width_over2;
+    const int s0 = job.s0, s1 = job.s1;
+    const int32_t *ypath = job.ypath;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nprod = (nthreads >> 5) - nb;
+
+    // positions touched by the tile, rounded out to whole blocks.  The search path is monotone (x or y advances
+    // by one per anti-diagonal), so the first / last diagonal bound every band offset of the tile.
+    const int bf = ypath[d_first] - w, bl = ypath[d_last] - w;
+    const int ylo = (bf >> 1) * 2, yhi = ((bl + B - 1) >> 1) * 2 + 1;
+    const int xlo = ((d_first - (bf + B - 1)) >> 1) * 2, xhi = ((d_last - bl) >> 1) * 2 + 1;
+    const int NX = xhi - xlo + 1, NY = yhi - ylo + 1, HX = NX >> 1, HY = NY >> 1;
+    const int rows_cap = svx_p2_rows_cap(B);
+    if (NX <= 0 || NY <= 0 || NX + NY > rows_cap) return;    // not a search path (an earlier level failed: status_d says so)
+    const int stage_floats = K * rows_cap * YS;
+    // after the ring: per staged row {source float offset from v0 / v1 (-1: zero row), byte offset in a stage};
+    // then the mbarriers
+    int2 *rowtab = reinterpret_cast<int2 *>(tile + (size_t)nstages * stage_floats);
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(rowtab + K * rows_cap);     // full[nstages], empty[nstages]
+    const int xstride = HX * XS;       // floats between overlaps in the x region
+    const int ystride = NY * YS;
+    const int ybase = K * HX * XS;     // the y region follows the x region
+
+    // x: slot k * NX + p is position xlo + p of overlap k, written into pair row p / 2 at float 2 d + (p & 1);
+    // y: slot K * NX + k * NY + q is position ylo + 2 q (q < HY) or ylo + 2 (q - HY) + 1 of overlap k
+    const int xrows = K * NX, yrows = K * NY;
+    for (int r = tid; r < xrows + yrows; r += nthreads) {
+        int off = -1, dst;
+        if (r < xrows) {
+            const int k = r / NX, p = r - k * NX, seg = xlo + p;
+            if (k < job.k0 && seg >= 0 && seg < s0) off = (int)(((size_t)k * s0 + seg) * dim);
+            dst = (k * xstride + (p >> 1) * XS + (p & 1)) * (int)sizeof(float);
+        } else {
+            const int r2 = r - xrows;
+            const int k = r2 / NY, q = r2 - k * NY;
+            const int seg = ylo + (q < HY ? 2 * q : 2 * (q - HY) + 1);
+            if (k < job.k1 && seg >= 0 && seg < s1) off = (int)(((size_t)k * s1 + seg) * dim);
+            dst = (ybase + r2 * YS) * (int)sizeof(float);
+        }
+        rowtab[r] = make_int2(off, dst);
+    }
+    if (tid < 2 * nstages) mbar_init(bars + 8 * tid, tid < nstages ? 32 * nprod : nb);
+    __syncthreads();
+    const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
+    const int slices = dim / BC;
+
+    if (warp >= nb) {
+        // ---- producers ----------------------------------------------------------------------------------------
+        const int pw = warp - nb;
+        const char *gx = reinterpret_cast<const char *>(job.v0), *gy = reinterpret_cast<const char *>(job.v1);
+        constexpr int XR = 32 / BC;            // x rows per warp instruction (4-byte copies, lane = d)
+        constexpr int YR = 32 / (BC / 4);      // y rows per warp instruction (16-byte copies)
+        const int xd = lane % BC, xsub = lane / BC;
+        const int yc = lane % (BC / 4), ysub = lane / (BC / 4);
+        for (int sl = 0; sl < slices; ++sl) {
+            const int s = sl % nstages;
+            if (sl >= nstages) mbar_wait(bars + 8 * (nstages + s), (unsigned)((sl / nstages - 1) & 1));
+            const unsigned buf = tile_u32 + (unsigned)(s * stage_floats * (int)sizeof(float));
+            // eight table entries are fetched before the eight copies they describe are issued: one shared-memory
+            // latency per batch instead of one per copy
+            constexpr int UB = 8;
+            const unsigned xdst = buf + (unsigned)(8 * xd);
+            const long long xsrc = (long long)(sl * BC + xd) * 4;
+            for (int r0 = pw * XR + xsub; r0 < xrows; r0 += UB * nprod * XR) {
+                int2 ent[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int r = r0 + u * nprod * XR;
+                    ent[u] = r < xrows ? rowtab[r] : make_int2(-2, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    if (ent[u].x == -2) continue;
+                    const char *gp = gx + (ent[u].x < 0 ? 0ll : (long long)ent[u].x * 4 + xsrc);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(xdst + (unsigned)ent[u].y), "l"(gp), "r"(ent[u].x < 0 ? 0 : 4));
+                }
+            }
+            const unsigned ydst = buf + (unsigned)(16 * yc);
+            const long long ysrc = (long long)(sl * BC + 4 * yc) * 4;
+            for (int r0 = pw * YR + ysub; r0 < yrows; r0 += UB * nprod * YR) {
+                int2 ent[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int r = r0 + u * nprod * YR;
+                    ent[u] = r < yrows ? rowtab[xrows + r] : make_int2(-2, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    if (ent[u].x == -2) continue;
+                    const char *gp = gy + (ent[u].x < 0 ? 0ll : (long long)ent[u].x * 4 + ysrc);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ydst + (unsigned)ent[u].y), "l"(gp), "r"(ent[u].x < 0 ? 0 : 16));
+                }
+            }
+            mbar_arrive_cp_async(bars + 8 * s);
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        return;
+    }
+
+    // ---- consumers: this thread's block ----------------------------------------------------------------------
+    const int yi = warp;
+    const int e = e_first + lane;
+    const int dA = 2 * e, dB = 2 * e + 1, dC = 2 * e + 2;
+    const bool vA = dA >= 0 && dA < A, vB = dB >= 0 && dB < A, vC = dC >= 0 && dC < A;
+    const int bA = vA ? ypath[dA] - w : 0, bB = vB ? ypath[dB] - w : 0, bC = vC ? ypath[dC] - w : 0;
+    // smallest Y with a band cell on one of the three diagonals: even yy on dA, both parities on dB, odd yy on dC
+    int ymin = INT_MAX;
+    if (vA) ymin = min(ymin, (bA + 1) >> 1);
+    if (vB) ymin = min(ymin, bB >> 1);
+    if (vC) ymin = min(ymin, bC >> 1);
+    const int Y = ymin + yi, X = e - Y;
+    const int yy0 = 2 * Y, xx0 = 2 * X;
+    unsigned inband = 0;               // bit c: cell c is a band cell; c = 0 (xx0, yy0), 1 (xx0+1, yy0), 2 (xx0, yy0+1), 3 (xx0+1, yy0+1)
+    int bslot[4] = {0, 0, 0, 0};
+    if (vA) { const int b = yy0 - bA; if (b >= 0 && b < B) { inband |= 1u; bslot[0] = b; } }
+    if (vB) {
+        const int b = yy0 - bB;
+        if (b >= 0 && b < B) { inband |= 2u; bslot[1] = b; }
+        if (b + 1 >= 0 && b + 1 < B) { inband |= 4u; bslot[2] = b + 1; }
+    }
+    if (vC) { const int b = yy0 + 1 - bC; if (b >= 0 && b < B) { inband |= 8u; bslot[3] = b; } }
+    const int xs = (xx0 - xlo) >> 1, ys = (yy0 - ylo) >> 1;       // pair row / even-half row of the block
+    const bool active = inband != 0 && xs >= 0 && xs < HX && ys >= 0 && ys < HY;
+    const bool warp_active = __any_sync(0xffffffffu, active);
+
+    u64 acc_e[T], acc_o[T];            // {(xx0, y), (xx0 + 1, y)} for y = yy0 / yy0 + 1, per type
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc_e[t] = acc_o[t] = 0ull;
+    const u64 one2 = pack2(one, one), nz2 = pack2(nz, nz);
+    // inactive lanes of an active warp read the block of lane-clamped rows (always staged) and drop the result
+    const int xs_c = min(max(xs, 0), HX - 1), ys_c = min(max(ys, 0), HY - 1);
+
+    for (int sl = 0; sl < slices; ++sl) {
+        const int s = sl % nstages;
+        mbar_wait(bars + 8 * s, (unsigned)((sl / nstages) & 1));
+        if (warp_active) {
+            const float *buf = tile + (size_t)s * stage_floats;
+            const float *px = buf + (size_t)xs_c * XS;
+            const float *pye = buf + ybase + (size_t)ys_c * YS;
+            const float *pyo = pye + (size_t)HY * YS;
+#pragma unroll 2
+            for (int d = 0; d < BC; d += DV) {
+                float ye[K][DV], yo[K][DV];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (DV == 4) {
+                        const float4 a = *reinterpret_cast<const float4 *>(pye + j * ystride + d);
+                        const float4 b = *reinterpret_cast<const float4 *>(pyo + j * ystride + d);
+                        ye[j][0] = a.x; ye[j][1] = a.y; ye[j][DV - 2] = a.z; ye[j][DV - 1] = a.w;
+                        yo[j][0] = b.x; yo[j][1] = b.y; yo[j][DV - 2] = b.z; yo[j][DV - 1] = b.w;
+                    } else {
+                        const float2 a = *reinterpret_cast<const float2 *>(pye + j * ystride + d);
+                        const float2 b = *reinterpret_cast<const float2 *>(pyo + j * ystride + d);
+                        ye[j][0] = a.x; ye[j][1] = a.y;
+                        yo[j][0] = b.x; yo[j][1] = b.y;
+                    }
+                }
+                int t = 0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    u64 xp[DV];           // {x[xx0][d + q], x[xx0 + 1][d + q]}
+                    {
+                        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(px + i * xstride + 2 * d);
+                        xp[0] = a.x; xp[1] = a.y;
+                        if (DV == 4) {
+                            const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(px + i * xstride + 2 * d + 4);
+                            xp[DV - 2] = b.x; xp[DV - 1] = b.y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; i + j <= K - 1; ++j, ++t) {
+#pragma unroll
+                        for (int q = 0; q < DV; ++q) {
+                            acc_e[t] = mac2<EXACT>(acc_e[t], xp[q], ye[j][q], one2, nz2);
+                            acc_o[t] = mac2<EXACT>(acc_o[t], xp[q], yo[j][q], one2, nz2);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * (nstages + s));
+    }
+    if (!active) return;
+
+    // ---- cost formula + store (dp_core.pyx:259-260), anti-diagonal-major (A, T, B) ----------------------------
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (!((inband >> c) & 1)) continue;
+        const int i = c & 1, j = c >> 1;
+        const int xx = xx0 + i, yy = yy0 + j, d = 2 * e + i + j;
+        const bool inside = xx >= 0 && xx < s0 && yy >= 0 && yy < s1;
+        float *out = job.costs + (size_t)d * T * B + bslot[c];
+        int t = 0;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int ky = 0; kx + ky <= K - 1; ++ky, ++t) {
+                float lo, hi;
+                unpack2(j ? acc_o[t] : acc_e[t], lo, hi);
+                float cst = INFINITY;
+                if (inside)
+                    cst = svx_band_cost(i ? hi : lo, kx + 1, ky + 1, job.n0[(size_t)kx * s0 + xx], job.n1[(size_t)ky * s1 + yy]);
+                out[(size_t)t * B] = cst;
+            }
+    }
+}
+
+template <int K, int BC, int DV>
+int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, int nstages, int nprod, cudaStream_t st)
+{
+    const int nb = band / 2 + 1;
+    if (nprod < 1) nprod = 1;
+    while (nprod > 1 && 32 * (nb + nprod) > svx_p2_max_threads(K)) --nprod;
+    const int threads = 32 * (nb + nprod);
+    const int rows_cap = svx_p2_rows_cap(band);
+    const size_t stage_bytes = (size_t)K * rows_cap * (BC + 4) * sizeof(float);
+    const size_t table = (size_t)K * rows_cap * sizeof(int2) + 2 * 8 * 8;
+    while (nstages > 2 && nstages * stage_bytes + table > 225 * 1024) --nstages;
+    const size_t smem = nstages * stage_bytes + table;
+    if (threads > svx_p2_max_threads(K) || smem > 225 * 1024 || dim % BC) return -1;
+    const int emax = (max_alen - 1) >> 1;                          // block-diagonals -1 .. emax
+    dim3 grid((emax + 2 + kNE - 1) / kNE, nj);
+    if (mode == SVX_COST_EXACT) {
+        auto kern = k_banded_costs_p2<K, BC, DV, true>;
+        SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, 1.0f, -0.0f);
+    } else {
+        auto kern = k_banded_costs_p2<K, BC, DV, false>;
+        SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, 1.0f, -0.0f);
+    }
+    SVX_LAUNCH_CHECK();
+    return SVX_OK;
+}
+
+}  // namespace
+
+int svx_launch_costs_p2(int K, const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, int bc,
+                        int nstages, int nprod, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (band & 1) return -1;
+    if (nstages < 2) nstages = 2;
+    if (nstages > 8) nstages = 8;
+#define P2(KK, BCC, DVV) return launch_p2_t<KK, BCC, DVV>(jobs_d, nj, max_alen, band, dim, mode, nstages, nprod, st)
+    switch (K) {
+        case 1: if (bc == 32) P2(1, 32, 4); else P2(1, 16, 4);
+        case 2: if (bc == 32) P2(2, 32, 4); else P2(2, 16, 4);
+        case 3: if (bc == 32) P2(3, 32, 4); else P2(3, 16, 4);
+        case 4: if (bc == 32) P2(4, 32, 4); else P2(4, 16, 4);
+        case 5: if (bc == 32) P2(5, 32, 4); else P2(5, 16, 4);
+        case 6: P2(6, 16, 2);
+        case 7: P2(7, 16, 2);
+        default: return -1;
+    }
+#undef P2
+}

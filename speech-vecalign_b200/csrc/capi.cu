@@ -38,6 +38,8 @@ extern "C" int svx_sizeof_job(int which)
         case 6: return (int)sizeof(SvxAlignRec);
         case 7: return (int)sizeof(SvxLevelJob);
         case 8: return (int)sizeof(SvxGatherJob);
+        case 9: return (int)sizeof(SvxAlignParams);
+        case 10: return (int)sizeof(SvxPlanInfo);
         default: return -1;
     }
 }
