@@ -255,11 +255,13 @@ def double_resolution(alignments):
 # ----------------------------------------------------------------------------- a15
 def vecalign(vecs0, vecs1, final_alignment_types, del_percentile_frac, width_over2,
              max_size_full_dp, costs_sample_size, num_samps_for_norm, norms0=None, norms1=None,
-             core=None, fast_host=False, timings=None):
+             core=None, fast_host=False, timings=None, penalties=None):
     """dp_utils.py:381-537 vecalign.  Same arguments and same ``stack`` result; ``core`` selects
     the native module (default: the C port; tests also pass the reference's compiled dp_core),
     ``fast_host`` swaps the per-row Python loops of a3/a4 for bit-identical vectorised numpy,
-    ``timings`` (dict) receives the reference's phase names (:419-529)."""
+    ``timings`` (dict) receives the reference's phase names (:419-529), ``penalties`` ({depth: value},
+    tests only) replaces the deletion penalty of those levels after the knob has been sampled (the RNG
+    stream is consumed as always) - how a parity test follows a case past a DeletionKnob tie."""
     core = core or _port_core
     tm = timings if timings is not None else {}
     if width_over2 < 3:
@@ -308,6 +310,8 @@ def vecalign(vecs0, vecs1, final_alignment_types, del_percentile_frac, width_ove
         lv['del_knob'] = sample_cost_knob(core, lv['v0'][0, :, :], lv['v1'][0, :, :],
                                           lv['n0'][0, :], lv['n1'][0, :], costs_sample_size, keep=lv)
         lv['del_penalty'] = lv['del_knob'].percentile_frac_to_del_penalty(del_percentile_frac)
+        if penalties is not None and d in penalties:
+            lv['del_penalty'] = type(lv['del_penalty'])(penalties[d])
     tm['Compute deletion penalties'] = perf_counter() - t0
 
     top = stack[depth_max]

@@ -1165,7 +1165,7 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
         static const bool use_p2 = !per_cell && !strcmp(which, "p2");
         static const int p2_bc = getenv("SVX_P2_BC") ? atoi(getenv("SVX_P2_BC")) : 16;
         static const int p2_stages = getenv("SVX_P2_STAGES") ? atoi(getenv("SVX_P2_STAGES")) : 4;
-        static const int p2_prod = getenv("SVX_P2_PRODUCERS") ? atoi(getenv("SVX_P2_PRODUCERS")) : 2;
+        static const int p2_prod = getenv("SVX_P2_PRODUCERS") ? atoi(getenv("SVX_P2_PRODUCERS")) : 4;   // clamped to 12 warps per CTA
         static const int p2_mink = getenv("SVX_P2_MINK") ? atoi(getenv("SVX_P2_MINK")) : 2;   // K = 1 (coarse levels, one type) is copy-bound
         if (standard && use_p2 && K >= p2_mink && K <= 7)
             rc = svx_launch_costs_p2(K, jobs_d + jb0, nj, max_alen, j0.band, dim, mode, p2_bc, p2_stages, p2_prod, st);

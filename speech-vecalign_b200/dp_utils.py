@@ -11,18 +11,24 @@ for parity work, ``cost_mode`` ('exact' | 'fast' | 'tc': fast + the coarsest-lev
 as a 3xTF32 tcgen05 GEMM).
 
 Semantics kept from the reference: the global ``np.random`` stream is consumed in the reference's
-order; ``width_over2 < 3`` is raised to 3 (:391-393); torch CUDA inputs are normalised in place
-(:396-397).  Deviation (documented in DESIGN.md): numpy inputs are not written back unless
-``writeback=True`` (the reference's callers never reuse them).
+order; ``width_over2 < 3`` is raised to 3 (:391-393); the inputs are normalised IN PLACE (:396-397):
+torch CUDA tensors directly, writable numpy arrays by copying the normalised rows back
+(``writeback=True``, the default of ``vecalign``; ``writeback=False`` skips the device->host copy for
+callers that do not reuse the arrays - the reference's own callers never do).  Host torch tensors are
+an extension of the interface and are left untouched.
+
+``vecalign_batch`` is not re-entrant per device: concurrent calls from several Python threads serialise
+on a lock around the pinned staging ring and the side streams.
 """
 import logging
 import os
+import threading
 
 import numpy as np
 import torch
 
 from . import capi
-from .engine import BatchRun, records_to_alignments
+from .engine import BatchRun, WidenJobs, host_threads, records_to_alignments
 
 logger = logging.getLogger('vecalign')
 
@@ -53,15 +59,13 @@ def _side_stream(dev, name):
 _STAGE_SLOT = 64 << 20
 _STAGE = {"slots": [], "events": [], "next": 0}
 _STAGE_MIN = 4 << 20                      # smaller arrays are not worth a slot round trip
+_LOCK = threading.RLock()                 # the staging ring and the side streams are process-wide
 
 
 def _stage_threads():
     if os.environ.get("SVX_STAGE_THREADS"):
         return max(1, int(os.environ["SVX_STAGE_THREADS"]))
-    try:
-        return max(1, min(16, len(os.sched_getaffinity(0))))
-    except Exception:
-        return max(1, min(16, os.cpu_count() or 1))
+    return host_threads(16)                  # this rank's share of the host cores
 
 
 def _stage_slot():
@@ -96,6 +100,32 @@ def _staged_copy(src_ptr, nbytes, dst):
         ev.record(stream)
         _STAGE["events"][i] = ev
         off += n
+
+
+def _copy_back(t, h):
+    """device tensor -> writable numpy array of the same shape (the reference normalises its inputs in place,
+    dp_utils.py:396-397): through the pinned ring, multi-threaded host copy out of each slot."""
+    flat = t.reshape(-1).view(torch.uint8)
+    nbytes = flat.numel()
+    if not h.flags.c_contiguous or nbytes < _STAGE_MIN or h.dtype != np.float32 or t.dtype != torch.float32:
+        h[...] = t.cpu().numpy()
+        return
+    nthreads = _stage_threads()
+    off, pending = 0, []
+    while off < nbytes or pending:
+        while off < nbytes and len(pending) < 4:
+            n = min(_STAGE_SLOT, nbytes - off)
+            i = _stage_slot()
+            slot = _STAGE["slots"][i]
+            slot[:n].copy_(flat[off:off + n], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(t.device))
+            _STAGE["events"][i] = ev
+            pending.append((i, off, n, ev))
+            off += n
+        i, o, n, ev = pending.pop(0)
+        ev.synchronize()
+        capi.check(capi.lib().svx_host_memcpy(h.ctypes.data + o, _STAGE["slots"][i].data_ptr(), n, nthreads), "svx_host_memcpy")
 
 
 def _to_device(v, dev):
@@ -135,26 +165,31 @@ def _widen(pairs_dev, dev):
     if not todo:
         return pairs_dev, None
     out = [list(pr) for pr in pairs_dev]
-    jobs = np.zeros(len(todo), dtype=capi.GATHER)
-    for j, (i, s) in enumerate(todo):
+    srcs, dsts = [], []
+    for i, s in todo:
         src = pairs_dev[i][s]
         dst = torch.empty(src.shape, dtype=torch.float32, device=dev)
         out[i][s] = dst
-        jobs[j]["rows"], jobs[j]["out"] = src.data_ptr(), dst.data_ptr()
-        jobs[j]["k"], jobs[j]["n"], jobs[j]["nrows"], jobs[j]["is_fp16"] = src.shape[0], src.shape[1], src.shape[0] * src.shape[1], 1
-    stage = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).pin_memory()
-    jd = torch.empty(stage.numel() + 16, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    capi.check(capi.lib().svx_upload_pinned(jd.data_ptr(), stage.data_ptr(), stage.numel(), stream), "svx_upload_pinned")
-    capi.check(capi.lib().svx_gather_doc_embedding(jd.data_ptr(), capi.hptr(jobs), len(todo), int(pairs_dev[0][0].shape[2]), stream),
-               "svx_gather_doc_embedding")
-    # the launches above are asynchronous: the caller keeps `stage` (pinned) and `jd` alive until it has synchronised
-    return [tuple(pr) for pr in out], (stage, jd, jobs, pairs_dev)
+        srcs.append(src)
+        dsts.append(dst)
+    job = WidenJobs(srcs, dsts, int(pairs_dev[0][0].shape[2]), dev)
+    job.run()
+    # the launches above are asynchronous: the caller keeps `job` (pinned descriptors, sources) alive until it has synchronised
+    return [tuple(pr) for pr in out], job
 
 
 def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                    costs_sample_size, num_samps_for_norm, cost_mode="exact", debug=False, writeback=False,
                    norms0=None, norms1=None, sync=True, output="stack", seeds=None, streams=None):
+    with _LOCK:
+        return _vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
+                               costs_sample_size, num_samps_for_norm, cost_mode, debug, writeback, norms0, norms1, sync,
+                               output, seeds, streams)
+
+
+def _vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
+                    costs_sample_size, num_samps_for_norm, cost_mode, debug, writeback, norms0, norms1, sync, output,
+                    seeds, streams):
     """Align many document pairs in one pass over the GPU.
 
     pairs: sequence of (vecs0, vecs1), each (K, N, D) fp32 numpy array or torch tensor (host or
@@ -166,6 +201,10 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
     makes every pair's result independent of batch order and of the multi-GPU partition.
     streams: pair groups enqueued on separate CUDA streams (default 4 for batches of >= 8 pairs);
     pairs are independent, so results do not depend on it.
+    A pair whose traceback fails on the device (the reference's IndexError / 'traceback bug',
+    dp_utils.py:123-124) raises in stack mode; with output="records" its entry carries the non-zero
+    'status' and the other pairs of the batch are returned normally (seg_align writes those and skips
+    the failing one).
     """
     if width_over2 < 3:
         logger.warning('width_over2 was set to %d, which does not make sense. increasing to 3.', width_over2)
@@ -279,7 +318,7 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
             cur.wait_stream(_side_stream(dev, ("chunk", c)))
     run = runs[0]
     if not sync:
-        run._keepalive = keepalive
+        run._keepalive = (keepalive, dv)        # the kernels are still running: inputs and descriptors stay alive with the run
         return run
     res = []
     if _tr:
@@ -290,12 +329,18 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
     for r_ in runs:
         res.extend(r_.results())
     _mark("results read")
+    if writeback:
+        for (t0, t1), (h0, h1) in zip(dv, hosts):
+            if h0 is not None and h0.flags.writeable:
+                _copy_back(t0, h0)
+            if h1 is not None and h1.flags.writeable:
+                _copy_back(t1, h1)
+    if output == "records":
+        return res
     for p, r in enumerate(res):
         if r["status"]:
             # the reference fails here with IndexError / 'traceback bug' (dp_utils.py:123-124)
             raise Exception('traceback bug (device status %d for pair %d)' % (r["status"], p))
-    if output == "records":
-        return res
     stacks = []
     for p, r in enumerate(res):
         al, sc = records_to_alignments(r["recs"])
@@ -305,19 +350,15 @@ def vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_over
         if debug:
             _fill_debug(st, run, p, dv[p], final_alignment_types)
         stacks.append(st)
-    if writeback:
-        for (t0, t1), (h0, h1) in zip(dv, hosts):
-            if h0 is not None and h0.flags.writeable:
-                h0[...] = t0.cpu().numpy()
-            if h1 is not None and h1.flags.writeable:
-                h1[...] = t1.cpu().numpy()
     return stacks
 
 
 def vecalign(vecs0, vecs1, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
              costs_sample_size, num_samps_for_norm, norms0=None, norms1=None, cost_mode="exact", debug=False,
-             writeback=False):
-    """Reference signature (dp_utils.py:381-390) + keyword-only extras; returns the ``stack``."""
+             writeback=True):
+    """Reference signature (dp_utils.py:381-390) + keyword-only extras; returns the ``stack``.  Like the
+    reference (:396-397) it leaves vecs0 / vecs1 normalised: numpy arrays get the normalised rows copied
+    back unless writeback=False."""
     return vecalign_batch([(vecs0, vecs1)], final_alignment_types, del_percentile_frac, width_over2,
                           max_size_full_dp, costs_sample_size, num_samps_for_norm, cost_mode=cost_mode,
                           debug=debug, writeback=writeback, norms0=norms0, norms1=norms1)[0]

@@ -127,6 +127,41 @@ class Plan:
             pass
 
 
+def workspace_bytes(params, n0, n1):
+    """(device arena bytes, host staging bytes) of a batch - svx_workspace_bytes."""
+    n0 = np.ascontiguousarray(n0, dtype=np.int32)
+    n1 = np.ascontiguousarray(n1, dtype=np.int32)
+    a, h = np.zeros(1, np.int64), np.zeros(1, np.int64)
+    capi.check(capi.lib().svx_workspace_bytes(capi.hptr(params), int(n0.shape[0]), capi.hptr(n0), capi.hptr(n1), capi.hptr(a), capi.hptr(h)),
+               "svx_workspace_bytes")
+    return int(a[0]), int(h[0])
+
+
+class WidenJobs:
+    """fp16 (K, N, D) device tensors -> fp32 working tensors with one launch of svx_gather_doc_embedding (identity
+    table: a widening copy that also zeroes rows containing NaNs, as make_doc_embedding does,
+    utils/embedding_utils.py:196-200).  The descriptors are uploaded once; run() can be repeated."""
+
+    def __init__(self, srcs, dsts, dim, device):
+        self.n, self.dim, self.dev = len(srcs), int(dim), device
+        jobs = np.zeros(self.n, dtype=capi.GATHER)
+        for j, (src, dst) in enumerate(zip(srcs, dsts)):
+            jobs[j]["rows"], jobs[j]["out"] = src.data_ptr(), dst.data_ptr()
+            jobs[j]["k"], jobs[j]["n"], jobs[j]["nrows"], jobs[j]["is_fp16"] = src.shape[0], src.shape[1], src.shape[0] * src.shape[1], 1
+        self.jobs = jobs
+        self._stage = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).pin_memory() if self.n else None
+        self._dev = torch.empty(max(jobs.nbytes, 16) + 16, dtype=torch.uint8, device=device)
+        self._keep = (srcs, dsts)
+        if self.n:
+            capi.check(capi.lib().svx_upload_pinned(self._dev.data_ptr(), self._stage.data_ptr(), self._stage.numel(),
+                                                    torch.cuda.current_stream(device).cuda_stream), "svx_upload_pinned")
+
+    def run(self):
+        if self.n:
+            capi.check(capi.lib().svx_gather_doc_embedding(self._dev.data_ptr(), capi.hptr(self.jobs), self.n, self.dim,
+                                                           torch.cuda.current_stream(self.dev).cuda_stream), "svx_gather_doc_embedding")
+
+
 def fallback_del_penalty(frac):
     """dp_utils.py:315-321: with an empty side the knob is built from [0, .5, 1] on [0, 1] (host twin of
     svx_del_knob; what svx_plan_bind presets every level's penalty to)."""
@@ -383,13 +418,12 @@ class BatchRun:
     def fetch_vecs(self, r, side):
         k = self.k0 if side == 0 else self.k1
         s = int(self.rs0[r] if side == 0 else self.rs1[r])
-        ptr = int(self.vec0_ptr[r] if side == 0 else self.vec1_ptr[r])
         n = k * s * self.dim
         if n == 0:
             return np.zeros((k, s, self.dim), dtype=np.float32)
         if self.rec_level[r] == 0:
             raise ValueError("level-0 vectors live in the caller's tensors")
-        off = ptr - self.base
+        off = self.off["vec0" if side == 0 else "vec1"][r]
         return self._get(off, n * 4, np.float32).reshape(k, s, self.dim).copy()
 
 

@@ -189,7 +189,7 @@ def run(args):
     logger.info("shard %d/%d: %d document pairs", rank, nshard, len(jobs))
 
     budget = args.batch_gb * 2 ** 30
-    done, i = 0, 0
+    done, i, failed = 0, 0, 0
     while i < len(jobs):
         batch, used = [], 0.0
         while i < len(jobs) and (not batch or used + k * sum(sizes[i]) * eu.EMBED_DIM * 4 <= budget):
@@ -201,6 +201,12 @@ def run(args):
                              args.num_samps_for_norm, cost_mode=args.cost_mode, output="records",
                              seeds=[pair_seed(item, args.seed) for item in batch])
         for item, r in zip(batch, res):
+            if r["status"]:
+                # the reference raises here (IndexError / 'traceback bug', dp_utils.py:123-124) and stops; a batch
+                # driver keeps every other pair and leaves this one without an output file
+                logger.error("traceback failed for %s (device status %d): no output written", item["out"].name, r["status"])
+                failed += 1
+                continue
             al, sc = records_to_alignments(r["recs"])
             tmp = item["out"].with_suffix(".txt.tmp")
             with open(tmp, "w") as f:
@@ -210,7 +216,9 @@ def run(args):
                 write_filtered(filt_dir / item["out"].name, filter_by_cost(al, sc, args.max_cost))
         done += len(batch)
         logger.info("shard %d: %d/%d pairs aligned", rank, done, len(jobs))
-    return done
+    if failed:
+        logger.error("shard %d: %d document pairs failed", rank, failed)
+    return done - failed
 
 
 def main(argv=None):

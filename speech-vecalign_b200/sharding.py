@@ -4,8 +4,8 @@ Document pairs are closed computations (seg_align/align.py:206-230 aligns them o
 the path shards by pair with NO data-path collective: each rank aligns its shard on its own GPU
 and the per-pair results (a few KB) are gathered on the host.  The reference's own sharding helper
 (utils/mp_utils.py:7-16 get_shard_range) cuts contiguous ranges; here pairs are length-balanced
-with the LPT rule on an estimate of the per-pair work, and bucketed by (levels, path length) so
-that batched launches have uniform trip counts.
+with the LPT rule on an estimate of the per-pair work (bench.py's config-4 arm, the seg_align driver
+and align_sharded below all partition with it).
 
 Host RNG: with ``seeds`` (one per pair) every pair draws from its own np.random stream, so results
 do not depend on the partition; without seeds the caller must draw in input order on one rank.
@@ -21,7 +21,7 @@ def estimate_work(n0, n1, alignment_max_size, search_buffer_size=5, dim=1024, ma
     k = alignment_max_size - 1
     t = alignment_max_size * (alignment_max_size - 1) / 2
     band = 2 * (np.ceil(k / 2) + search_buffer_size)
-    return (t + 1) * (n0 + n1 + 3) * band * dim + 8 * k * (n0 + n1) * dim + min(max_size_full_dp, 300) ** 2 * dim
+    return (t + 1) * (n0 + n1 + 3) * band * dim + 8 * k * (n0 + n1) * dim + float(max_size_full_dp) ** 2 * dim
 
 
 def lpt_partition(work, nranks):
@@ -36,14 +36,6 @@ def lpt_partition(work, nranks):
         shards[r].append(int(i))
         load[r] += work[i]
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
-
-
-def bucket_by_shape(depth, a_len, step=256):
-    """Group pair indices by (number of levels, ceil(A/step)) — uniform kernel trip counts."""
-    keys = {}
-    for i, (d, a) in enumerate(zip(depth, a_len)):
-        keys.setdefault((int(d), int(-(-int(a) // step))), []).append(i)
-    return keys
 
 
 def gather_in_order(local_results, local_indices, total, group=None, dst=0):

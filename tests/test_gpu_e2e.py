@@ -248,3 +248,90 @@ def test_many_to_one_types(svb, oracle):
     np.random.seed(4)
     got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), types, 0.2, w, 300, 20000, 100, debug=True)
     _compare(ref, got)
+
+
+def test_numpy_inputs_are_normalised_in_place_by_default(svb, oracle):
+    """dp_utils.py:396-397: the reference leaves its inputs normalised; vecalign() copies the rows back
+    into writable numpy arrays (also through the pinned ring for large arrays) unless writeback=False."""
+    from speech_vecalign_b200 import synth
+    for n0, n1, k in ((120, 125, 3), (1500, 1400, 4)):        # below / above the staging threshold
+        v0, v1 = synth.synth_pair(n0, n1, k, seed=4)
+        a0, a1 = v0.copy(), v1.copy()
+        keep = v0.copy()
+        np.random.seed(1)
+        svb.dp_utils.vecalign(a0, a1, oracle.alignment_types(k + 1), 0.2, 7, 300, 20000, 100)
+        r0, r1 = v0.copy(), v1.copy()
+        oracle.unit_rows(r0, fast=True)
+        oracle.unit_rows(r1, fast=True)
+        assert np.array_equal(a0, r0) and np.array_equal(a1, r1)
+        b0 = v0.copy()
+        np.random.seed(1)
+        svb.dp_utils.vecalign(b0, v1.copy(), oracle.alignment_types(k + 1), 0.2, 7, 300, 20000, 100, writeback=False)
+        assert np.array_equal(b0, keep)
+
+
+def test_production_path_levels_match_oracle(svb, oracle):
+    """The non-debug path stores only overlap 0 of the coarser levels (SvxLevelJob.keep = 1) - a different prologue
+    code path from the debug stack's keep = k.  Its overlap-0 rows and norms of every level are fetched from the
+    arena of a production run and compared with the oracle: rows bit-exact, norms <= 2.4e-7."""
+    import torch
+    from speech_vecalign_b200 import synth
+    a, k = 5, 4
+    v0, v1 = synth.synth_pair(1300, 1210, k, seed=9)
+    args = (oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100)
+    np.random.seed(3)
+    ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+    np.random.seed(3)
+    run = svb.vecalign_batch([(v0.copy(), v1.copy())], *args, sync=False)
+    torch.cuda.synchronize()
+    assert not run.keep_dense_csum and len(ref) == int(run.nlev[0]) == 4
+    for d in range(len(ref)):
+        r = run.level_record(0, d)
+        for side, (kv, kn) in enumerate((("v0", "n0"), ("v1", "n1"))):
+            s = ref[d][kv].shape[1]
+            if d > 0:
+                assert np.array_equal(run.fetch_vecs(r, side)[0], ref[d][kv][0]), (d, side)
+            norms = run.fetch("norms0" if side == 0 else "norms1", r, (k, s), np.float32)
+            rows = slice(0, k) if d == 0 else slice(0, 1)
+            assert np.max(np.abs(norms[rows] - ref[d][kn][rows])) <= 2.4e-7, (d, side)
+        assert abs(run.results()[0]["del_penalty"][d] - ref[d]["del_penalty"]) <= 1e-6 * max(1.0, abs(ref[d]["del_penalty"]))
+    from speech_vecalign_b200.engine import records_to_alignments
+    al, sc = records_to_alignments(run.results()[0]["recs"])
+    assert same_alignments(al, ref[0]["final_alignments"])
+
+
+@pytest.mark.parametrize("sbs", [6, 7, 8])
+def test_alignment_max_size_9_wide_buffers(svb, oracle, sbs):
+    """a = 9 (K = 8) with search buffers 6-8: band + K <= 32 selects the warp-per-band DP, whose chunk plan exceeds
+    shared memory at these sizes - the launcher must fall through to the generic kernel (round-1 advisor finding)."""
+    ref, got = _run_both(svb, oracle, 260, 250, 9, seed=90 + sbs, search_buffer_size=sbs, dim=128)
+    _compare(ref, got)
+
+
+def test_many_to_one_50_default_of_the_cli(svb, oracle):
+    """The reference CLI's --many_to_one default (const=50: 50 types, width_over2 = 30, band 60) runs through the
+    generic cost and DP kernels (round-1 advisor finding: bands >= 46 were rejected)."""
+    from speech_vecalign_b200 import synth
+    m = 50
+    types = svb.make_many_to_one_alignment_types(m)
+    v0, v1 = synth.synth_pair(150, 40, m, dim=128, seed=78)
+    v1 = v1[:1].copy()
+    w = math.ceil(m / 2) + 5
+    np.random.seed(4)
+    ref = oracle.vecalign(v0.copy(), v1.copy(), types, 0.2, w, 300, 20000, 100, fast_host=True)
+    np.random.seed(4)
+    got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), types, 0.2, w, 300, 20000, 100, debug=True)
+    _compare(ref, got)
+
+
+def test_num_samps_for_norm_above_fused_limit(svb, oracle):
+    """num_samps_for_norm > 2048 exceeds the fused prologue's scratch: the planner switches to the unfused launchers."""
+    from speech_vecalign_b200 import synth
+    v0, v1 = synth.synth_pair(400, 390, 3, dim=128, seed=5)
+    args = (oracle.alignment_types(4), 0.2, 7, 300, 20000, 2500)
+    np.random.seed(2)
+    ref = oracle.vecalign(v0.copy(), v1.copy(), *args, fast_host=True)
+    np.random.seed(2)
+    got = svb.dp_utils.vecalign(v0.copy(), v1.copy(), *args)
+    assert same_alignments(got[0]["final_alignments"], ref[0]["final_alignments"])
+    assert np.max(np.abs(got[0]["alignment_scores"] - ref[0]["alignment_scores"])) <= 1e-4

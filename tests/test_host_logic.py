@@ -210,74 +210,150 @@ def test_path_len_matches_reference_glue(svb, oracle, c0, c1, t0, t1):
     oracle.extend_to(up, t0, t1)
     assert svb.capi.lib().svx_path_len(c0, c1, t0, t1, 1) == len(oracle.search_path(up))
     assert svb.capi.lib().svx_path_len(c0, c1, c0, c1, 0) == len(oracle.search_path(al))
-    from speech_vecalign_b200 import engine
-    assert int(engine.path_len(c0, c1, t0, t1, 1)) == len(oracle.search_path(up))
 
 
 # ------------------------------------------------------------------------------------------------
-def test_planner_level_sizes(svb):
+# The planner lives in libsvx.so (csrc/plan.cu, svx_plan_*): it is host code until the plan is bound to
+# device memory, so everything below runs without a GPU.
+# ------------------------------------------------------------------------------------------------
+def _plan(svb, n0, n1, k0, k1, a_types, sample_size=20000, nsfn=100, full=300, w=7, dim=128):
     from speech_vecalign_b200 import engine
-    depth, s0, s1 = engine.level_sizes([237, 2000, 20000, 0, 5, 299], [217, 2000, 20000, 5, 301, 302], 300)
+    prm = engine.make_params(k0, k1, dim, a_types, 0.2, w, full, sample_size, nsfn)
+    return engine.Plan(prm, n0, n1)
+
+
+def test_planner_level_sizes(svb, oracle):
+    """dp_utils.py:403-408 level sizes and the search-path lengths that follow from the path glue."""
+    pl = _plan(svb, [237, 2000, 20000, 0, 5, 299], [217, 2000, 20000, 5, 301, 302], 4, 4, oracle.alignment_types(5))
+    depth, first, rs0, rs1, A = (pl.array(k) for k in ("depth", "first", "rs0", "rs1", "A"))
     assert list(depth) == [0, 3, 7, 0, 0, 1]
-    assert list(s0[1][:4]) == [2000, 1000, 500, 250] and s0[2][7] == 156
-    assert s0[5][1] == 149 and s1[5][1] == 151
+    assert list(rs0[first[1]:first[1] + 4]) == [2000, 1000, 500, 250] and rs0[first[2] + 7] == 156
+    assert rs0[first[5] + 1] == 149 and rs1[first[5] + 1] == 151
+    # banded levels: A = len(search path built from the next coarser level); the coarsest level has none
+    L = svb.capi.lib()
+    assert A[first[0]] == L.svx_path_len(237, 217, 237, 217, 0)
+    assert A[first[1]] == L.svx_path_len(1000, 1000, 2000, 2000, 1) == 4003 and A[first[1] + 3] == 0
+    assert A[first[5]] == L.svx_path_len(149, 151, 299, 302, 1)
+    assert int(pl.info["band"]) == 14 and int(pl.info["per0"]) == 25
+
+
+def _python_draws(rs0, rs1, first, nlev, k0, k1, nsfn, ss, rs):
+    """The reference's call order, spelled out: per pair, for each level the n0 draws (K1 calls
+    over range(size1), dp_utils.py:346), then the n1 draws; then per level the knob draws x, y (:301-302)."""
+    per1, per0 = -(-nsfn // k1), -(-nsfn // k0)
+    out = {}
+    for p in range(len(first)):
+        f, n = int(first[p]), int(nlev[p])
+        r_ = rs(p)
+        for r in range(f, f + n):
+            a, b = int(rs0[r]), int(rs1[r])
+            if b:
+                out[("idx0", r)] = np.stack([r_.randint(0, b, per1) for _ in range(k1)])
+            if a:
+                out[("idx1", r)] = np.stack([r_.randint(0, a, per0) for _ in range(k0)])
+        for r in range(f, f + n):
+            a, b = int(rs0[r]), int(rs1[r])
+            if a > 0 and b > 0 and a * b >= ss:
+                out[("xi", r)] = r_.randint(0, a, ss)
+                out[("yi", r)] = r_.randint(0, b, ss)
+    return out, per0, per1
 
 
 @pytest.mark.parametrize("n0,n1,a", [(237, 217, 4), (700, 650, 5), (90, 80, 6), (0, 5, 4), (3, 2000, 4)])
 def test_planner_replays_reference_rng_stream(svb, oracle, n0, n1, a):
-    """draw_samples() must leave np.random in exactly the state the reference's vecalign leaves it in
-     — checked against the oracle driver, which is pinned to the reference."""
-    from speech_vecalign_b200 import engine, synth
+    """svx_plan_draw_stream must leave np.random in exactly the state the reference's vecalign leaves it in
+     - checked against the oracle driver, which is pinned to the reference."""
+    from speech_vecalign_b200 import synth
     k = a - 1
     v0, v1 = synth.synth_pair(n0, n1, k, dim=128, seed=1)
     np.random.seed(77)
     oracle.vecalign(v0, v1, oracle.alignment_types(a), 0.2, math.ceil(k / 2) + 5, 300, 20000, 100, fast_host=True)
-    want = np.random.get_state()[1].copy()
-    depth, S0, S1 = engine.level_sizes([n0], [n1], 300)
-    nlev = depth + 1
+    want = np.random.get_state()
+    pl = _plan(svb, [n0], [n1], k, k, oracle.alignment_types(a), w=math.ceil(k / 2) + 5)
+    stage = np.zeros(max(int(pl.info["host_bytes"]), 16), dtype=np.uint8)
+    ptrs = np.zeros(1, dtype=np.uint64)
+    pl.bind(4096, stage.ctypes.data, ptrs, ptrs)          # the arena address only enters the descriptors
     np.random.seed(77)
-    engine.draw_samples(S0[0, :nlev[0]], S1[0, :nlev[0]], np.array([0]), nlev, k, k, 100, 20000, False, False)
-    assert np.array_equal(np.random.get_state()[1], want)
+    pl.draw(None)
+    got = np.random.get_state()
+    assert np.array_equal(got[1], want[1]) and got[2] == want[2]
 
 
 @pytest.mark.parametrize("seeded", [False, True])
-def test_draws_into_staging_match_reference_order(svb, seeded):
-    """draw_samples_into (vectorised call list; C MT19937 replay for per-pair seeds) must produce
-    exactly the numbers of the straightforward draw_samples loop, which is itself pinned to the
-    reference's stream above — including the global stream's final state."""
-    from speech_vecalign_b200 import engine
+def test_draws_into_staging_match_reference_order(svb, oracle, seeded):
+    """The C planner's draws (global stream continued in C, or one MT19937 stream per pair seed) land in the staging
+    block exactly where the descriptors point and equal numpy's numbers in the reference's call order."""
     n0 = [237, 700, 90, 0, 3, 2000, 1]
     n1 = [217, 650, 80, 5, 2000, 2000, 1]
     k0, k1, nsfn, ss = 3, 4, 100, 20000
-    depth, S0, S1 = engine.level_sizes(n0, n1, 300)
-    nlev = depth + 1
-    first = np.concatenate([[0], np.cumsum(nlev)[:-1]])
-    rp = np.repeat(np.arange(len(n0)), nlev)
-    rl = np.arange(int(nlev.sum())) - first[rp]
-    rs0, rs1 = S0[rp, rl], S1[rp, rl]
+    types = [(1, 1), (1, 2), (2, 1)]
+    pl = _plan(svb, n0, n1, k0, k1, types, sample_size=ss, nsfn=nsfn)
+    first, nlev, rs0, rs1 = (pl.array(k) for k in ("first", "nlev", "rs0", "rs1"))
     seeds = [11 + 3 * i for i in range(len(n0))] if seeded else None
     np.random.seed(5)
-    idx0, idx1, knob, per0, per1 = engine.draw_samples(rs0, rs1, first, nlev, k0, k1, nsfn, ss, False, False, seeds=seeds)
-    state_ref = np.random.get_state()[1].copy()
-    R = rs0.shape[0]
-    has_draw = (rs0 > 0) & (rs1 > 0) & (rs0 * rs1 >= ss)
-    assert [k is not None for k in knob] == list(has_draw)
-    ar = engine._Arena()
-    off = {"idx0": ar.take(np.full(R, k1 * per1 * 4)), "idx1": ar.take(np.full(R, k0 * per0 * 4)),
-           "xi": ar.take(np.where(has_draw, ss * 4, 0)), "yi": ar.take(np.where(has_draw, ss * 4, 0))}
-    stage = np.zeros(ar.top, dtype=np.uint8)
+    want, per0, per1 = _python_draws(rs0, rs1, first, nlev, k0, k1, nsfn, ss,
+                                     (lambda p: np.random.RandomState(seeds[p])) if seeded else (lambda p: np.random))
+    state_ref = np.random.get_state()
+    stage = np.zeros(int(pl.info["host_bytes"]), dtype=np.uint8)
+    ptrs = np.zeros(len(n0), dtype=np.uint64)
+    pl.bind(4096, stage.ctypes.data, ptrs, ptrs)
     np.random.seed(5)
-    knob2 = engine.draw_samples_into(stage, off, rs0, rs1, rp, rl, k0, k1, per0, per1, ss, has_draw, False, False, seeds)
+    pl.draw(seeds)
     if not seeded:
-        assert np.array_equal(np.random.get_state()[1], state_ref)
-    for r in range(R):
-        got0 = stage[off["idx0"][r]:off["idx0"][r] + k1 * per1 * 4].view(np.int32).reshape(k1, per1)
-        got1 = stage[off["idx1"][r]:off["idx1"][r] + k0 * per0 * 4].view(np.int32).reshape(k0, per0)
-        assert np.array_equal(got0, idx0[r]) and np.array_equal(got1, idx1[r]), r
-        if knob[r] is not None:
-            assert np.array_equal(knob2[r][0], knob[r][0]) and np.array_equal(knob2[r][1], knob[r][1]), r
-        else:
-            assert knob2[r] is None
+        got = np.random.get_state()
+        assert np.array_equal(got[1], state_ref[1]) and got[2] == state_ref[2]
+    off = {k: pl.array(k) for k in ("idx0", "idx1", "xi", "yi")}
+    assert (int(pl.info["per0"]), int(pl.info["per1"])) == (per0, per1)
+    has_draw = pl.array("has_draw")
+    for r in range(len(rs0)):
+        for key, rows, per in (("idx0", k1, per1), ("idx1", k0, per0)):
+            if (key, r) in want:
+                got = stage[off[key][r]:off[key][r] + rows * per * 4].view(np.int32).reshape(rows, per)
+                assert np.array_equal(got, want[(key, r)]), (key, r)
+        assert bool(has_draw[r]) == (("xi", r) in want)
+        for key in ("xi", "yi"):
+            if (key, r) in want:
+                assert np.array_equal(stage[off[key][r]:off[key][r] + 4 * ss].view(np.int32), want[(key, r)]), (key, r)
+
+
+def test_plan_matches_workspace_query_and_rejects_bad_types(svb, oracle):
+    """svx_workspace_bytes == the plan's own sizes; the reference's overlap check (dp_core.pyx:204-209) is kept."""
+    from speech_vecalign_b200 import engine
+    L = svb.capi.lib()
+    n0 = np.array([237, 2000], dtype=np.int32)
+    n1 = np.array([217, 1900], dtype=np.int32)
+    prm = engine.make_params(4, 4, 1024, oracle.alignment_types(5), 0.2, 7, 300, 20000, 100)
+    pl = engine.Plan(prm, n0, n1)
+    a, h = np.zeros(1, np.int64), np.zeros(1, np.int64)
+    assert L.svx_workspace_bytes(prm.ctypes.data, 2, n0.ctypes.data, n1.ctypes.data, a.ctypes.data, h.ctypes.data) == 0
+    assert (int(a[0]), int(h[0])) == (int(pl.info["arena_bytes"]), int(pl.info["host_bytes"]))
+    bad = engine.make_params(2, 4, 1024, oracle.alignment_types(5), 0.2, 7, 300, 20000, 100)
+    with pytest.raises(svb.capi.SvxError, match="x overlaps requrested"):
+        engine.Plan(bad, n0, n1)
+    # the default penalty of an empty pair is the reference's fallback knob (dp_utils.py:315-321)
+    assert float(pl.info["fallback_del_penalty"]) == engine.fallback_del_penalty(0.2)
+
+
+@pytest.mark.parametrize("B", [2, 6, 14, 16, 18, 24])
+def test_packed_cost_kernel_block_cover(B):
+    """banded_p2.cu maps band/2 + 1 warps onto the 2x2 position blocks of a block-diagonal: enumerate every band
+    offset pattern (the path moves 0 or 1 in y per anti-diagonal) and check that Ymin and the block count hold."""
+    for b0 in range(-5, 6):
+        for s1 in (0, 1):
+            for s2 in (0, 1):
+                b1, b2 = b0 + s1, b0 + s1 + s2
+                for vA in (0, 1):
+                    for vB in (0, 1):
+                        for vC in (0, 1):
+                            ys = set()
+                            for ok, b, par in ((vA, b0, (0,)), (vB, b1, (0, 1)), (vC, b2, (1,))):
+                                if ok:
+                                    ys |= {(yy - yy % 2) // 2 for yy in range(b, b + B) if yy % 2 in par}
+                            if not ys:
+                                continue
+                            cand = ([(b0 + 1) >> 1] if vA else []) + ([b1 >> 1] if vB else []) + ([b2 >> 1] if vC else [])
+                            assert min(cand) == min(ys)
+                            assert max(ys) - min(ys) + 1 <= B // 2 + 1
 
 
 def test_c_randint_replay_equals_numpy(svb):
