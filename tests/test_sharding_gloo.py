@@ -95,9 +95,3 @@ def test_gather_without_process_group_restores_order():
     from speech_vecalign_b200 import sharding
     out = sharding.gather_in_order(["c", "a"], [2, 0], 3)
     assert out == ["a", None, "c"]
-
-
-def test_bucket_by_shape():
-    from speech_vecalign_b200 import sharding
-    b = sharding.bucket_by_shape([0, 1, 1, 0], [400, 1300, 1290, 420], step=256)
-    assert b[(0, 2)] == [0, 3] and b[(1, 6)] == [1, 2]
