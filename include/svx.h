@@ -371,6 +371,20 @@ SVX_API int svx_align_batch(const SvxAlignParams *params, int npairs, const int3
                             SvxAlignRec *recs_out, const int64_t *rec_begin, int32_t *nrecs_out, double *del_penalty_out,
                             int32_t *status_out, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Margin scoring of aligned segment pairs: replaces compute_sim_with_nonflat_idx
+ * (svecalign/postprocess/score_align.py:124-161) with an exact flat k-nearest-neighbour search on the
+ * tensor cores (tcgen05 fp16 x fp16 -> fp32, TMA-fed; the reference's faiss-gpu flat index stores fp16):
+ *   score_i = a_i / b_i (margin 0, "ratio") or a_i - b_i (1, "distance"),  a_i = <x_i, y_i> on L2-normalised rows,
+ *   b_i = mean of (2 - avg_k |x_i - y|^2) / 2 over the k nearest y in ybase and the same for y_i in xbase.
+ * xbase_d / ybase_d = NULL: the pairs' own rows are the searched collections (the shipped example).
+ * Rows are fp32 or fp16 (is_fp16), dim a multiple of 64, 1 <= k <= 16.  Asynchronous on `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+SVX_API int svx_margin_workspace_bytes(int n, int n_xbase, int n_ybase, int dim, int64_t *bytes);
+SVX_API int svx_margin_scores(const void *x_d, const void *y_d, int n, const void *xbase_d, int n_xbase, const void *ybase_d,
+                              int n_ybase, int dim, int is_fp16, int k, int margin, float *scores_d, void *workspace_d,
+                              int64_t workspace_bytes, void *stream);
+
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);

@@ -15,6 +15,10 @@ Fixtures
                            seeded inputs: every array the reference returned.
   e2e.json                 reference final alignments / scores / del_penalty for seeded synthetic
                            pairs (inputs are regenerated from the seed by speech_vecalign_b200.synth).
+  margin/                  step 6.7 (postprocess/score_align.py) on the shipped example: the 347 + 347 vectors the
+                           reference's two `Flat` faiss indexes hold (read out of Flat.populate.idx: 45-byte header,
+                           then raw fp32 rows whose values are fp16-representable - stored here as fp16) and the
+                           margin scores the reference shipped for them (align_0.7_clean_cat3_min1s_margin).
 """
 import json
 import math
@@ -157,8 +161,22 @@ def e2e():
     json.dump({"numpy": np.__version__, "cases": cases}, open(os.path.join(HERE, "e2e.json"), "w"))
 
 
+def margin():
+    dst = os.path.join(HERE, "margin")
+    os.makedirs(dst, exist_ok=True)
+    for lang in ("en", "de"):
+        raw = open(f"{EX}/align_0.7_clean_cat3_min1s_embed_indexes/en-de/{lang}/Flat.populate.idx", "rb").read()
+        n = (len(raw) - 45) // (1024 * 4)
+        vec = np.frombuffer(raw[45:45 + n * 1024 * 4], dtype=np.float32).reshape(n, 1024)
+        assert n == 347 and len(raw) == 45 + n * 4096 and np.array_equal(vec.astype(np.float16).astype(np.float32), vec)
+        np.save(f"{dst}/{lang}.index_vectors.f16.npy", vec.astype(np.float16))
+    shutil.copy(f"{EX}/align_0.7_clean_cat3_min1s_margin/en-de/{NAME}_en-{NAME}_de.txt", f"{dst}/shipped_margin.txt")
+    print("margin: 2 x 347 index vectors + shipped scores")
+
+
 if __name__ == "__main__":
     example()
+    margin()
     functions()
     e2e()
     print("golden fixtures written to", HERE)

@@ -233,3 +233,33 @@ def test_oracle_equals_live_reference(oracle, ref_du, n0, n1, a, seed):
                 assert list(val) == list(g)
             else:
                 assert val == g, (d, key)
+
+
+# ------------------------------------------------------------------------------------------------
+# Margin scoring (oracle/margin_oracle.py restates postprocess/score_align.py:118-161)
+# ------------------------------------------------------------------------------------------------
+def _margin_fixture():
+    g = os.path.join(GOLDEN, "margin")
+    x = np.load(os.path.join(g, "en.index_vectors.f16.npy")).astype(np.float32)
+    y = np.load(os.path.join(g, "de.index_vectors.f16.npy")).astype(np.float32)
+    shipped = np.array([float(ln.rsplit(":", 1)[1]) for ln in open(os.path.join(g, "shipped_margin.txt"))])
+    return x, y, shipped
+
+
+def test_margin_oracle_reproduces_the_shipped_scores():
+    """The reference's own known answer for step 6.7: the 347 margin scores shipped under
+    example/voxpopuli/align_0.7_clean_cat3_min1s_margin, from the vectors its two Flat indexes hold.  The reference
+    computed them with faiss-gpu in fp16 (`--gpu_type fp16-shard`): exact search reproduces them to 1.2e-4 (fp32
+    storage) / 1.9e-4 (fp16 storage); bar 2.5e-4 on scores of magnitude 1.1 - 1.4."""
+    from oracle import margin_oracle as mo
+    x, y, shipped = _margin_fixture()
+    assert x.shape == y.shape == (347, 1024) and shipped.shape == (347,)
+    for dt in (np.float16, np.float32):
+        got = mo.margin_scores(x, y, 16, "ratio", index_dtype=dt)
+        assert np.max(np.abs(got - shipped)) <= 2.5e-4
+    # the distance margin differs from the ratio margin only in the last step (score_align.py:155-158)
+    a = np.einsum("ij,ij->i", mo.normalize_L2(x.copy()).astype(np.float64), mo.normalize_L2(y.copy()).astype(np.float64))
+    ratio, dist = mo.margin_scores(x, y, 16, "ratio"), mo.margin_scores(x, y, 16, "distance")
+    assert np.allclose(a / ratio, a - dist, atol=1e-6)
+    with pytest.raises(ValueError):
+        mo.margin_scores(x, y, 16, "cosine")
