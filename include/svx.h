@@ -385,6 +385,14 @@ SVX_API int svx_margin_scores(const void *x_d, const void *y_d, int n, const voi
                               int n_ybase, int dim, int is_fp16, int k, int margin, float *scores_d, void *workspace_d,
                               int64_t workspace_bytes, void *stream);
 
+/* Host only: the (max_overlaps, nlines[d]) int32 row tables of make_doc_embedding (utils/embedding_utils.py:106-203,
+ * overlap_segments=True as seg_align/align.py:222 passes) for `ndocs` documents, read straight from their segment and
+ * concatenation files on `nthreads` threads; ignore_pairs[d] = n_ignore[d] (start, end) pairs (vecalign.py:43-52 files),
+ * NULL for none.  tables_out[d] feeds SvxGatherJob.table; nrows_out[d] = rows the concatenation file names. */
+SVX_API int svx_host_overlap_tables(int ndocs, const char *const *seg_paths, const char *const *cat_paths,
+                                    const int32_t *const *ignore_pairs, const int32_t *n_ignore, int max_overlaps,
+                                    int32_t *const *tables_out, const int32_t *nlines, int32_t *nrows_out, int nthreads);
+
 /* misc */
 SVX_API int svx_version(void);
 SVX_API const char *svx_last_error_string(void);

@@ -127,6 +127,7 @@ def lib():
         "svx_plan_enqueue": [vp, ci, ci, ci, vp],
         "svx_plan_fetch": [vp, vp, vp, vp, vp, vp, vp],
         "svx_workspace_bytes": [vp, ci, vp, vp, vp, vp],
+        "svx_host_overlap_tables": [ci, vp, vp, vp, vp, ci, vp, vp, vp, ci],
         "svx_margin_workspace_bytes": [ci, ci, ci, ci, vp],
         "svx_margin_scores": [vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, ctypes.c_int64, vp],
         "svx_align_batch": [vp, ci, vp, vp, vp, vp, vp, vp, ctypes.c_int64, vp, ctypes.c_int64, ci, vp, vp, vp, vp, vp, vp],
@@ -158,6 +159,7 @@ EXPORTED_SYMBOLS = [
     "svx_plan_create", "svx_plan_destroy", "svx_plan_info", "svx_plan_array", "svx_plan_bind", "svx_plan_draw_seeded",
     "svx_plan_draw_stream", "svx_plan_upload", "svx_plan_launcher_name", "svx_plan_enqueue", "svx_plan_fetch",
     "svx_workspace_bytes", "svx_align_batch", "svx_margin_workspace_bytes", "svx_margin_scores",
+    "svx_host_overlap_tables",
 ]
 
 

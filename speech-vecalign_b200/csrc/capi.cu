@@ -178,3 +178,118 @@ extern "C" int svx_host_memcpy(void *dst, const void *src, long long nbytes, int
     for (auto &th : pool) th.join();
     return SVX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// (K, N) row tables of make_doc_embedding for many documents at once (the input contract of the path,
+// utils/embedding_utils.py:106-203 with overlap_segments=True, the mode seg_align/align.py:222 uses):
+//   table[j, i + j] = row of the embedding file whose key is "<first token of line i> <second token of line i+j>",
+//   -1 (a zero row) for keys the concatenation file does not hold, for (i, i+j) pairs in the ignore list and every
+//   longer concatenation from the same start (:124-126), and for positions before the document start.
+// Lines are stripped like Python's str.strip(); an empty line becomes '[BLANK_LINE]' (:29-35); the concatenation
+// file maps a stripped line to the FIRST row that carries it (:97-101).  Documents run on `nthreads` host threads.
+// The Python twin is embedding_utils.overlap_row_table (tests compare the two).
+// ---------------------------------------------------------------------------------------------
+#include <string>
+#include <unordered_map>
+
+namespace {
+
+inline bool is_ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || c == 0x1c || c == 0x1d || c == 0x1e || c == 0x1f || c == 0x85 || c == 0xa0; }
+
+bool read_lines(const char *path, std::vector<std::string> &out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    std::string buf;
+    char chunk[1 << 16];
+    size_t n;
+    while ((n = fread(chunk, 1, sizeof(chunk), f)) > 0) buf.append(chunk, n);
+    fclose(f);
+    size_t pos = 0;
+    while (pos < buf.size()) {
+        size_t e = buf.find('\n', pos);
+        if (e == std::string::npos) e = buf.size();
+        size_t a = pos, b = e;
+        while (a < b && (unsigned char)buf[a] < 0x80 && is_ws((unsigned char)buf[a])) ++a;
+        while (b > a && (unsigned char)buf[b - 1] < 0x80 && is_ws((unsigned char)buf[b - 1])) --b;
+        out.emplace_back(buf, a, b - a);
+        pos = e + 1;
+    }
+    return true;
+}
+
+// first / second whitespace-separated token of a line (str.split()); false if the line has fewer than `idx + 1`
+bool token(const std::string &s, int idx, std::string &tok)
+{
+    size_t p = 0;
+    for (int t = 0;; ++t) {
+        while (p < s.size() && (unsigned char)s[p] < 0x80 && is_ws((unsigned char)s[p])) ++p;
+        if (p >= s.size()) return false;
+        size_t q = p;
+        while (q < s.size() && !((unsigned char)s[q] < 0x80 && is_ws((unsigned char)s[q]))) ++q;
+        if (t == idx) { tok.assign(s, p, q - p); return true; }
+        p = q;
+    }
+}
+
+}  // namespace
+
+extern "C" int svx_host_overlap_tables(int ndocs, const char *const *seg_paths, const char *const *cat_paths,
+                                       const int32_t *const *ignore_pairs, const int32_t *n_ignore, int max_overlaps,
+                                       int32_t *const *tables_out, const int32_t *nlines, int32_t *nrows_out, int nthreads)
+{
+    if (ndocs <= 0) return SVX_OK;
+    if (!seg_paths || !cat_paths || !tables_out || !nlines || max_overlaps < 0) { svx_set_error("svx_host_overlap_tables: null argument"); return SVX_ERR_ARG; }
+    std::vector<int> status(ndocs, 0);
+    auto work = [&](int t, int nt) {
+        for (int d = t; d < ndocs; d += nt) {
+            std::vector<std::string> lines, cats;
+            if (!read_lines(seg_paths[d], lines) || !read_lines(cat_paths[d], cats)) { status[d] = 1; continue; }
+            if ((int)lines.size() != nlines[d]) { status[d] = 2; continue; }
+            std::unordered_map<std::string, int> key2row;
+            key2row.reserve(cats.size() * 2);
+            for (size_t i = 0; i < cats.size(); ++i) key2row.emplace(cats[i], (int)i);     // setdefault: first row wins
+            if (nrows_out) nrows_out[d] = (int32_t)cats.size();
+            const int n = (int)lines.size();
+            std::vector<std::string> t0(n), t1(n);
+            std::vector<char> ok0(n), ok1(n);
+            for (int i = 0; i < n; ++i) {
+                const std::string &ln = lines[i].empty() ? std::string("[BLANK_LINE]") : lines[i];
+                ok0[i] = token(ln, 0, t0[i]);
+                ok1[i] = token(ln, 1, t1[i]);
+            }
+            int32_t *tab = tables_out[d];
+            for (long long i = 0; i < (long long)max_overlaps * n; ++i) tab[i] = -1;
+            const int32_t *ign = ignore_pairs ? ignore_pairs[d] : nullptr;
+            const int nign = (ign && n_ignore) ? n_ignore[d] : 0;
+            std::string key;
+            for (int i = 0; i < n && status[d] == 0; ++i) {
+                for (int j = i; j < i + max_overlaps && j < n; ++j) {
+                    bool ignored = false;
+                    for (int q = 0; q < nign; ++q) if (ign[2 * q] == i && ign[2 * q + 1] == j) { ignored = true; break; }
+                    if (ignored) break;                                  // PAD from here on (embedding_utils.py:124-126)
+                    if (!ok0[i] || !ok1[j]) { status[d] = 3; break; }    // Python: IndexError on .split()[k]
+                    key.assign(t0[i]); key.push_back(' '); key.append(t1[j]);
+                    auto it = key2row.find(key);
+                    if (it != key2row.end()) tab[(size_t)(j - i) * n + j] = it->second;
+                }
+            }
+        }
+    };
+    int nt = nthreads < 1 ? 1 : nthreads;
+    if (nt > ndocs) nt = ndocs;
+    if (nt == 1) work(0, 1);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nt; ++t) pool.emplace_back(work, t, nt);
+        for (auto &th : pool) th.join();
+    }
+    for (int d = 0; d < ndocs; ++d)
+        if (status[d]) {
+            svx_set_error("svx_host_overlap_tables: document %d (%s): %s", d, seg_paths[d],
+                          status[d] == 1 ? "cannot read the segment / concatenation file" :
+                          status[d] == 2 ? "segment file changed length" : "a segment line has fewer than two fields");
+            return SVX_ERR_ARG;
+        }
+    return SVX_OK;
+}

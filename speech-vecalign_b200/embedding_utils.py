@@ -181,3 +181,87 @@ def make_doc_embedding_device(sent2id: dict, rows: np.ndarray, lines: List[str],
         if bad:
             logger.error("loaded %d vector(s) with nan values; reset to zero", bad)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched device path of the seg_align driver: many documents per call.  Host part (file reads, row tables in C on
+# several threads, rows packed into ONE pinned slab) and device part (one upload, ONE gather launch, one NaN-count
+# read-back per batch) are separate so that a loader thread can prepare batch b + 1 while the GPU aligns batch b.
+# ---------------------------------------------------------------------------------------------
+def open_embedding_rows(embed_file: str, use_stopes: bool = False, fp16_embed: bool = False) -> np.ndarray:
+    """load_embedding_rows without reading the file: a memory map in the on-disk dtype."""
+    if use_stopes:
+        return load_embedding_rows(embed_file, True, fp16_embed)
+    emb = np.memmap(embed_file, dtype=np.float16 if fp16_embed else np.float32, mode="r")
+    if emb.size == 0:
+        raise Exception('Got empty embedding file')
+    return emb.reshape(emb.shape[0] // EMBED_DIM, EMBED_DIM)
+
+
+def prepare_documents_host(docs, max_overlaps: int, use_stopes: bool, fp16_embed: bool, nthreads: int = 8):
+    """docs: list of dicts {seg, cat, emb, nlines, ignore (set of (start, end) or None)}.  Returns the host half of a
+    batch: pinned `slab` holding every document's embedding rows back to back (on-disk dtype), pinned `tables`
+    (concatenated (K, N) int32 row tables, svx_host_overlap_tables), and per-document offsets."""
+    import ctypes
+    import torch
+    from . import capi
+    L = capi.lib()
+    nd = len(docs)
+    rows = [open_embedding_rows(str(d["emb"]), use_stopes, fp16_embed) for d in docs]
+    dim = rows[0].shape[1] if nd else EMBED_DIM
+    is16 = [r.dtype == np.float16 for r in rows]
+    nbytes = np.array([r.shape[0] * r.shape[1] * r.dtype.itemsize for r in rows], dtype=np.int64)
+    row_off = np.concatenate([[0], np.cumsum((nbytes + 255) // 256 * 256)]).astype(np.int64)
+    nlines = np.array([d["nlines"] for d in docs], dtype=np.int32)
+    tab_off = np.concatenate([[0], np.cumsum(max_overlaps * nlines.astype(np.int64))]).astype(np.int64)
+    slab = torch.empty(max(int(row_off[-1]), 16), dtype=torch.uint8, pin_memory=True)
+    tables = torch.empty(max(int(tab_off[-1]), 4), dtype=torch.int32, pin_memory=True)
+    tnp = tables.numpy()
+    # row tables: C, all documents of the batch in one call
+    seg = (ctypes.c_char_p * nd)(*[str(d["seg"]).encode() for d in docs])
+    cat = (ctypes.c_char_p * nd)(*[str(d["cat"]).encode() for d in docs])
+    ign_arrays = [np.array(sorted(d["ignore"]), dtype=np.int32).reshape(-1, 2) if d.get("ignore") else np.zeros((0, 2), np.int32) for d in docs]
+    ign_ptrs = (ctypes.c_void_p * nd)(*[a.ctypes.data if a.size else None for a in ign_arrays])
+    n_ign = np.array([a.shape[0] for a in ign_arrays], dtype=np.int32)
+    out_ptrs = (ctypes.c_void_p * nd)(*[tnp.ctypes.data + 4 * int(tab_off[i]) for i in range(nd)])
+    nrows = np.zeros(nd, dtype=np.int32)
+    capi.check(L.svx_host_overlap_tables(nd, seg, cat, ign_ptrs, capi.hptr(n_ign), max_overlaps, out_ptrs, capi.hptr(nlines),
+                                         capi.hptr(nrows), nthreads), "svx_host_overlap_tables")
+    # rows -> pinned slab (reads the memory-mapped files), several threads per copy
+    base = slab.data_ptr()
+    for i, r in enumerate(rows):
+        if nbytes[i]:
+            src = r if r.flags.c_contiguous else np.ascontiguousarray(r)
+            capi.check(L.svx_host_memcpy(base + int(row_off[i]), src.ctypes.data, int(nbytes[i]), nthreads), "svx_host_memcpy")
+    return {"slab": slab, "tables": tables, "row_off": row_off, "tab_off": tab_off, "nlines": nlines, "is16": is16,
+            "nrows": np.array([r.shape[0] for r in rows], dtype=np.int32), "dim": dim, "k": max_overlaps}
+
+
+def gather_documents_device(host, device=None):
+    """Device half: uploads the slab and the tables (two copies), gathers every document's (K, N, D) fp32 overlap
+    tensor with ONE svx_gather_doc_embedding launch.  Returns (list of tensors, nan_rows int32 device tensor [ndocs],
+    keepalive) - read nan_rows after the batch has been synchronised anyway."""
+    import torch
+    from . import capi
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    nd = len(host["nlines"])
+    k, dim = host["k"], host["dim"]
+    slab_d = host["slab"].to(dev, non_blocking=True)
+    tab_d = host["tables"].to(dev, non_blocking=True)
+    out_off = np.concatenate([[0], np.cumsum(k * host["nlines"].astype(np.int64) * dim)]).astype(np.int64)
+    out = torch.empty(max(int(out_off[-1]), 1), dtype=torch.float32, device=dev)
+    nan_rows = torch.zeros(max(nd, 1), dtype=torch.int32, device=dev)
+    jobs = np.zeros(nd, dtype=capi.GATHER)
+    jobs["rows"] = slab_d.data_ptr() + host["row_off"][:-1].astype(np.uint64)
+    jobs["table"] = tab_d.data_ptr() + 4 * host["tab_off"][:-1].astype(np.uint64)
+    jobs["out"] = out.data_ptr() + 4 * out_off[:-1].astype(np.uint64)
+    jobs["nan_rows"] = nan_rows.data_ptr() + 4 * np.arange(nd, dtype=np.uint64)
+    jobs["k"], jobs["n"], jobs["nrows"], jobs["is_fp16"] = k, host["nlines"], host["nrows"], np.array(host["is16"], dtype=np.int32)
+    stage = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).pin_memory() if nd else None
+    jd = torch.empty(max(jobs.nbytes, 16) + 16, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if nd:
+        capi.check(capi.lib().svx_upload_pinned(jd.data_ptr(), stage.data_ptr(), stage.numel(), stream), "svx_upload_pinned")
+        capi.check(capi.lib().svx_gather_doc_embedding(jd.data_ptr(), capi.hptr(jobs), nd, dim, stream), "svx_gather_doc_embedding")
+    tensors = [out[int(out_off[i]):int(out_off[i + 1])].view(k, int(host["nlines"][i]), dim) for i in range(nd)]
+    return tensors, nan_rows, (slab_d, tab_d, jd, stage, jobs, out, host)

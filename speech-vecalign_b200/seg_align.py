@@ -11,6 +11,10 @@ Same command line (positional ``metadata out_dir``; ``--src_lang --tgt_lang --se
 ``--batch_gb`` of embeddings, every batch is one ``vecalign_batch`` call (one kernel launch per stage
 for all its pairs), and with several processes (``torchrun`` or ``--rank/--n_shard``) the pairs are
 length-balanced across GPUs; no collective is needed because every process writes its own files.
+The batches are pipelined: a loader thread reads the files of batch b + 1 (row tables built by
+svx_host_overlap_tables on several threads, embedding rows packed into one pinned slab in their on-disk
+dtype) while the GPU gathers and aligns batch b (one upload, one gather launch, one launch chain) and
+writer threads format the output files of batch b - 1.
 
 Additions: ``--skip_existing`` (the reference's slow stages do this, preprocess/segment.py:105-128),
 ``--seed`` (the reference draws from the unseeded global RNG; here pair i draws from
@@ -24,14 +28,16 @@ postprocess/filter_by_cost.py:39-87).
 import argparse
 import logging
 import os
+import time
 import zlib
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
 
 from . import embedding_utils as eu
 from .dp_utils import vecalign_batch
-from .engine import records_to_alignments
+from .engine import host_threads, records_to_alignments
 from .vecalign import load_ignore_index_file, make_alignment_types, print_alignments, width_over2_for
 
 logger = logging.getLogger("seg_align")
@@ -189,23 +195,32 @@ def run(args):
     logger.info("shard %d/%d: %d document pairs", rank, nshard, len(jobs))
 
     budget = args.batch_gb * 2 ** 30
-    done, i, failed = 0, 0, 0
+    batches, i = [], 0
     while i < len(jobs):
-        batch, used = [], 0.0
-        while i < len(jobs) and (not batch or used + k * sum(sizes[i]) * eu.EMBED_DIM * 4 <= budget):
+        lo, used = i, 0.0
+        while i < len(jobs) and (i == lo or used + k * sum(sizes[i]) * eu.EMBED_DIM * 4 <= budget):
             used += k * sum(sizes[i]) * eu.EMBED_DIM * 4
-            batch.append(jobs[i])
             i += 1
-        pairs = [load_pair(item, k, args, on_device=not args.host_gather) for item in batch]
-        res = vecalign_batch(pairs, types, args.del_percentile_frac, w, args.max_size_full_dp, args.costs_sample_size,
-                             args.num_samps_for_norm, cost_mode=args.cost_mode, output="records",
-                             seeds=[pair_seed(item, args.seed) for item in batch])
+        batches.append((lo, i))
+    nthreads = host_threads(16)
+
+    def load_host(lo, hi):
+        """host half of a batch (files -> pinned slab + row tables), run one batch ahead on the loader thread"""
+        docs = []
+        for item, (ns, nt) in zip(jobs[lo:hi], sizes[lo:hi]):
+            for side, n in (("src", ns), ("tgt", nt)):
+                ign = load_ignore_index_file(item[side + "_ign"]) if item[side + "_ign"] else None
+                docs.append({"seg": item[side + "_seg"], "cat": item[side + "_cat"], "emb": item[side + "_emb"], "nlines": n, "ignore": ign})
+        return eu.prepare_documents_host(docs, k, args.is_stopes_embed, args.fp16_embed, nthreads)
+
+    def write_batch(batch, res):
+        bad = 0
         for item, r in zip(batch, res):
             if r["status"]:
                 # the reference raises here (IndexError / 'traceback bug', dp_utils.py:123-124) and stops; a batch
                 # driver keeps every other pair and leaves this one without an output file
                 logger.error("traceback failed for %s (device status %d): no output written", item["out"].name, r["status"])
-                failed += 1
+                bad += 1
                 continue
             al, sc = records_to_alignments(r["recs"])
             tmp = item["out"].with_suffix(".txt.tmp")
@@ -214,10 +229,42 @@ def run(args):
             os.replace(tmp, item["out"])
             if args.max_cost is not None:                     # step 6.1 straight from the records
                 write_filtered(filt_dir / item["out"].name, filter_by_cost(al, sc, args.max_cost))
+        return bad
+
+    t_start = time.perf_counter()
+    done, failed, writes = 0, 0, []
+    loader = ThreadPoolExecutor(max_workers=1)
+    writer = ThreadPoolExecutor(max_workers=2)
+    pipelined = not args.host_gather
+    fut = loader.submit(load_host, *batches[0]) if (pipelined and batches) else None
+    for b, (lo, hi) in enumerate(batches):
+        batch = jobs[lo:hi]
+        if pipelined:
+            host = fut.result()
+            fut = loader.submit(load_host, *batches[b + 1]) if b + 1 < len(batches) else None
+            tensors, nan_rows, keep = eu.gather_documents_device(host)
+            pairs = [(tensors[2 * q], tensors[2 * q + 1]) for q in range(hi - lo)]
+        else:
+            pairs = [load_pair(item, k, args, on_device=False) for item in batch]
+        res = vecalign_batch(pairs, types, args.del_percentile_frac, w, args.max_size_full_dp, args.costs_sample_size,
+                             args.num_samps_for_norm, cost_mode=args.cost_mode, output="records",
+                             seeds=[pair_seed(item, args.seed) for item in batch])
+        if pipelined:
+            nbad = int(nan_rows.sum().item())                 # one read-back per batch (the batch has been synchronised)
+            if nbad:
+                logger.error("loaded %d vector(s) with nan values; reset to zero", nbad)
+            del tensors, pairs, keep
+        writes.append(writer.submit(write_batch, batch, res))
         done += len(batch)
         logger.info("shard %d: %d/%d pairs aligned", rank, done, len(jobs))
+    failed = sum(f.result() for f in writes)
+    loader.shutdown()
+    writer.shutdown()
     if failed:
         logger.error("shard %d: %d document pairs failed", rank, failed)
+    dt = time.perf_counter() - t_start
+    logger.info("shard %d: %d pairs, files to files in %.2f s (%.1f pairs/s)", rank, done - failed, dt, (done - failed) / max(dt, 1e-9))
+    run.last_stats = {"pairs": done - failed, "seconds": dt}
     return done - failed
 
 

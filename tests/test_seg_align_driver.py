@@ -157,6 +157,47 @@ def _synthetic_corpus(root, n_docs, k, rng):
             "--fp16_embed", "-a", str(k + 1), "--max_size_full_dp", "100", "--costs_sample_size", "4000"]
 
 
+def test_native_row_tables_equal_the_python_contract(tmp_path, svb):
+    """svx_host_overlap_tables (C, many documents per call, threads) == embedding_utils.overlap_row_table, the Python
+    restatement of make_doc_embedding's key lookups (utils/embedding_utils.py:106-203): the shipped example with its
+    ignore lists, and documents with unknown keys, blank lines and odd whitespace."""
+    import ctypes
+    from speech_vecalign_b200 import embedding_utils as eu, seg_align
+    from speech_vecalign_b200.vecalign import load_ignore_index_file
+    argv = _tree(tmp_path)
+    args = seg_align.build_parser().parse_args(argv)
+    _, jobs = seg_align.resolve_pairs(open(args.metadata), args)
+    docs = []
+    for side in ("src", "tgt"):
+        docs.append({"seg": jobs[0][side + "_seg"], "cat": jobs[0][side + "_cat"], "ign": load_ignore_index_file(jobs[0][side + "_ign"])})
+    odd = tmp_path / "odd"
+    odd.mkdir()
+    (odd / "seg.txt").write_text("0.0 1.5\n 1.5\t2.25 \r\n2.25 3.0 extra\n3.0 4.0\n4.0 5.5")
+    (odd / "cat.txt").write_text("0.0 1.5\n0.0 2.25\n0.0 1.5\n1.5 3.0\n\n3.0 5.5\n2.25 3.0\n")
+    docs.append({"seg": odd / "seg.txt", "cat": odd / "cat.txt", "ign": {(1, 2), (3, 3)}})
+    k = 5
+    lines = [open(d["seg"], "rt", encoding="utf-8").readlines() for d in docs]
+    want = []
+    for d, ln in zip(docs, lines):
+        key_to_row = {}
+        for i, line in enumerate(open(d["cat"], "rt", encoding="utf-8")):
+            key_to_row.setdefault(line.strip(), i)
+        want.append(eu.overlap_row_table(key_to_row, ln, k, ignore_indices=d["ign"], overlap_segments=True))
+    nd = len(docs)
+    nlines = np.array([len(ln) for ln in lines], dtype=np.int32)
+    outs = [np.full((k, int(n)), -7, dtype=np.int32) for n in nlines]
+    ign = [np.array(sorted(d["ign"]), dtype=np.int32).reshape(-1, 2) for d in docs]
+    for nthreads in (1, 3):
+        rc = svb.capi.lib().svx_host_overlap_tables(
+            nd, (ctypes.c_char_p * nd)(*[str(d["seg"]).encode() for d in docs]), (ctypes.c_char_p * nd)(*[str(d["cat"]).encode() for d in docs]),
+            (ctypes.c_void_p * nd)(*[a.ctypes.data for a in ign]), np.array([a.shape[0] for a in ign], dtype=np.int32).ctypes.data, k,
+            (ctypes.c_void_p * nd)(*[o.ctypes.data for o in outs]), nlines.ctypes.data, None, nthreads)
+        assert rc == 0, svb.capi.lib().svx_last_error_string()
+        for got, ref in zip(outs, want):
+            assert np.array_equal(got, ref)
+    assert (want[2] >= 0).sum() == 3 and (want[0] >= 0).sum() > 1000
+
+
 @pytest.mark.gpu
 def test_driver_batches_and_shards_synthetic_corpus(tmp_path, oracle):
     """Nine synthetic document pairs through the driver: small --batch_gb (several GPU batches), two shards
