@@ -352,6 +352,9 @@ SVX_API int svx_plan_draw_seeded(SvxPlan *plan, const uint32_t *seeds, int nthre
 SVX_API int svx_plan_draw_stream(SvxPlan *plan, uint32_t *key624, int32_t *pos);
 /* staging block -> arena; norms preset to 1.0 (dp_utils.py:356-357), counts and status cleared.  Asynchronous. */
 SVX_API int svx_plan_upload(SvxPlan *plan, int stage_is_pinned, void *stream);
+/* The same reset from a device copy of the staging block (host_bytes long): for callers that run several plans in one
+ * arena and restore each plan's descriptors and draws before its run without touching PCIe. */
+SVX_API int svx_plan_restore(SvxPlan *plan, const void *stage_copy_d, void *stream);
 SVX_API int svx_plan_launcher_name(const SvxPlan *plan, int launcher, char *buf, int cap);
 /* Enqueues launcher `launcher` (-1: the whole chain, in order) for pairs [pair_lo, pair_hi).  Asynchronous. */
 SVX_API int svx_plan_enqueue(const SvxPlan *plan, int launcher, int pair_lo, int pair_hi, void *stream);

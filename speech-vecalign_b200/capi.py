@@ -123,6 +123,7 @@ def lib():
         "svx_plan_draw_seeded": [vp, vp, ci],
         "svx_plan_draw_stream": [vp, vp, vp],
         "svx_plan_upload": [vp, ci, vp],
+        "svx_plan_restore": [vp, vp, vp],
         "svx_plan_launcher_name": [vp, ci, vp, ci],
         "svx_plan_enqueue": [vp, ci, ci, ci, vp],
         "svx_plan_fetch": [vp, vp, vp, vp, vp, vp, vp],
@@ -157,7 +158,7 @@ EXPORTED_SYMBOLS = [
     "svx_host_randint_seeded", "svx_upload_pinned", "svx_host_memcpy", "svx_version",
     "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
     "svx_plan_create", "svx_plan_destroy", "svx_plan_info", "svx_plan_array", "svx_plan_bind", "svx_plan_draw_seeded",
-    "svx_plan_draw_stream", "svx_plan_upload", "svx_plan_launcher_name", "svx_plan_enqueue", "svx_plan_fetch",
+    "svx_plan_draw_stream", "svx_plan_upload", "svx_plan_restore", "svx_plan_launcher_name", "svx_plan_enqueue", "svx_plan_fetch",
     "svx_workspace_bytes", "svx_align_batch", "svx_margin_workspace_bytes", "svx_margin_scores",
     "svx_host_overlap_tables",
 ]

@@ -2,20 +2,23 @@
 //   svx_dense_costs(mode = SVX_COST_TC)   (dp_core.pyx:36-77 make_dense_costs)
 //
 // costs[x, y] = 2 (1 - v0[x].v1[y]) / (1e-6 + n0[x] + n1[y]) is a true dense (s0 x 1024) . (1024 x s1)
-// contraction per document pair.  One CTA computes one 128 x 128 tile of one pair:
+// contraction per document pair, computed in 128 x 128 tiles.
 //
-//   TMA      cp.async.bulk.tensor.2d loads 128 rows x 32 floats (128 B, SWIZZLE_128B) of each operand
+// Persistent, warp-specialised CTAs (one per SM) walk the launch's 128 x 128 tiles:
+//   TMA      (warp 0) cp.async.bulk.tensor.2d loads 128 rows x 32 floats (128 B, SWIZZLE_128B) of each operand
 //            per k-slice into a 3-stage shared-memory ring, completion on an mbarrier; rows past the
 //            end of a document are zero-filled by the TMA unit.  One CUtensorMap per operand per
 //            pair, encoded on the host (svx_dense_tmaps_encode) and shipped with the job descriptors.
-//   split    all four warps split each fp32 operand element into hi = its upper 19 bits (exactly a
+//   split    (warps 2-5) each fp32 operand element is split into hi = its upper 19 bits (exactly a
 //            TF32 number, written back in place) and lo = a - hi (written to a second buffer with the
-//            same swizzled addressing), then fence.proxy.async so the tensor core sees the writes.
-//   tcgen05  one elected thread issues, per 8-wide k step, three kind::tf32 MMAs (hi.hi, hi.lo,
+//            same swizzled addressing), then fence.proxy.async so the tensor core sees the writes; a stage's
+//            `split` mbarrier hands it to the MMA warp - the split of slice k + 1 overlaps the MMAs of slice k.
+//   tcgen05  (warp 1, one thread) per 8-wide k step three kind::tf32 MMAs (hi.hi, hi.lo,
 //            lo.hi; the lo.lo term is < 2^-22 relative) accumulating the 128 x 128 fp32 tile in TMEM
-//            (128 columns), and commits to an mbarrier that releases the ring stage back to TMA.
-//   epilogue tcgen05.ld 32x32b brings each warp's 32 accumulator rows to registers; the cost formula
-//            is evaluated in double exactly as in the reference and stored with the raw dots.
+//            (three 128-column accumulators), and commits to an mbarrier that releases the ring stage back to TMA.
+//   epilogue (warps 2-5) tcgen05.ld 32x32b brings each warp's 32 accumulator rows to registers; the cost formula
+//            is evaluated in double exactly as in the reference and stored with the raw dots.  The accumulators are
+//            handed back to the MMA warp as soon as they have been read, before the formula of the last columns.
 //
 // 3xTF32 tolerance (tests/test_gpu_tensor_core.py): |dot - fp32 sequential dot| <= 4e-6 on unit
 // vectors, i.e. costs within 1e-5 absolute; the coarse alignment path is checked to stay identical.
@@ -101,25 +104,36 @@ __device__ __forceinline__ void split_tf32(float4 &v, float4 &lo)
     v = hi;
 }
 
-__global__ void __launch_bounds__(128, 1) k_dense_costs_tc(const SvxDenseJob *jobs, int dim)
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised, persistent: CTA b takes tiles b, b + gridDim.x, ... of the launch's (job, tile row, tile column)
+// grid.  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = splitters (raw fp32 k-slice -> hi / lo TF32 planes, in
+// shared memory, off the MMA warp's critical path) and, once a tile's accumulators are complete, its epilogue.  Three
+// mbarriers per ring stage: raw (TMA bytes landed) -> split (the four splitter warps are done, planes visible to the
+// async proxy) -> free (tcgen05.commit: the MMAs have read the stage); no CTA-wide barrier inside the k loop.
+constexpr int kTcThreads = 192;
+
+__global__ void __launch_bounds__(kTcThreads, 1) k_dense_costs_tc(const SvxDenseJob *jobs, int dim, int tiles_x, int tiles_y, int njobs)
 {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) unsigned long long bars[2 * kStages + 1];   // full[], free[], accumulator done
+    __shared__ __align__(8) unsigned long long bars[3 * kStages + 2];   // raw[], split[], free[], accumulators done, accumulators drained
     __shared__ unsigned tmem_slot;
-    const SvxDenseJob job = jobs[blockIdx.z];
-    const int x0 = blockIdx.y * kTM, y0 = blockIdx.x * kTN;
-    if (x0 >= job.s0 || y0 >= job.s1) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const unsigned tiles_u32 = smem_u32(tiles);
-    const unsigned bar_full = smem_u32(&bars[0]), bar_free = smem_u32(&bars[kStages]), bar_acc = smem_u32(&bars[2 * kStages]);
+    const unsigned bar_raw = smem_u32(&bars[0]), bar_split = smem_u32(&bars[kStages]), bar_free = smem_u32(&bars[2 * kStages]);
+    const unsigned bar_acc = smem_u32(&bars[3 * kStages]), bar_drained = smem_u32(&bars[3 * kStages + 1]);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_free + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_raw + 8 * s, 1); mbar_init(bar_split + 8 * s, 4); mbar_init(bar_free + 8 * s, 1); }
         mbar_init(bar_acc, 1);
+        mbar_init(bar_drained, 4);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_slot)), "n"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
     }
@@ -127,104 +141,142 @@ __global__ void __launch_bounds__(128, 1) k_dense_costs_tc(const SvxDenseJob *jo
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
     const unsigned tmem_d = tmem_slot;
-
     const int nk = dim / kTK;
-    auto issue_tma = [&](int ks) {
-        const int s = ks % kStages;
-        const unsigned base = tiles_u32 + s * kStageBytes;
-        mbar_expect_tx(bar_full + 8 * s, 2 * kTileBytes);
-        tma_load_2d(base, job.tmap0, bar_full + 8 * s, ks * kTK, x0);
-        tma_load_2d(base + kTileBytes, job.tmap1, bar_full + 8 * s, ks * kTK, y0);
+    const int per_job = tiles_x * tiles_y, ntiles = per_job * njobs;
+
+    // every role walks the same tile list and skips the tiles outside its job's matrix
+    auto tile_of = [&](int t, int &j, int &x0, int &y0) {
+        j = t / per_job;
+        const int r = t - j * per_job;
+        x0 = (r / tiles_x) * kTM;
+        y0 = (r % tiles_x) * kTN;
+        return x0 < jobs[j].s0 && y0 < jobs[j].s1;
     };
-    if (tid == 0)
-        for (int ks = 0; ks < kStages && ks < nk; ++ks) issue_tma(ks);
 
-    for (int ks = 0; ks < nk; ++ks) {
-        const int s = ks % kStages;
-        const unsigned ph = (ks / kStages) & 1;
-        mbar_wait(bar_full + 8 * s, ph);                       // both operand slices have landed
-        // hi/lo split, elementwise: the swizzled position of an element is the same in all four tiles
-        float4 *hi4 = reinterpret_cast<float4 *>(tiles + (size_t)s * kStageBytes);
-        float4 *lo4 = hi4 + 2 * kTileBytes / 16;
-#pragma unroll 4
-        for (int i = tid; i < 2 * kTileBytes / 16; i += 128) {
-            float4 v = hi4[i], lo;
-            split_tf32(v, lo);
-            hi4[i] = v;
-            lo4[i] = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-            const unsigned base = tiles_u32 + s * kStageBytes;
-            const unsigned a_hi = base, b_hi = base + kTileBytes, a_lo = base + 2 * kTileBytes, b_lo = base + 3 * kTileBytes;
-#pragma unroll
-            // The tensor core rounds toward zero each time it adds an MMA result into the fp32
-            // accumulator, so the error grows with the number of MMAs per accumulator.  The hi.hi
-            // products alternate between two accumulators (even / odd k-slices) and the two small
-            // cross terms (2^-11 of the main term) go to a third one; the epilogue adds the three.
-            const unsigned d_main = tmem_d + (unsigned)((ks & 1) * kTN);
-            const unsigned d_cross = tmem_d + (unsigned)(2 * kTN);
-            for (int k = 0; k < kTK / 8; ++k) {                // UMMA K = 8 tf32 = 32 bytes along the row
-                const unsigned off = k * 32;
-                umma_tf32(d_main, umma_desc(a_hi + off), umma_desc(b_hi + off), (ks >= 2) || k != 0);
-                umma_tf32(d_cross, umma_desc(a_hi + off), umma_desc(b_lo + off), (ks | k) != 0);
-                umma_tf32(d_cross, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
-            }
-            umma_commit(bar_free + 8 * s);                     // arrives when these MMAs have read the stage
-            if (ks == nk - 1) umma_commit(bar_acc);
-            // refill the stage consumed one iteration ago (its MMAs have had a whole iteration to drain)
-            const int kr = ks - 1 + kStages;
-            if (ks >= 1 && kr < nk) {
-                const int sr = (ks - 1) % kStages;
-                mbar_wait(bar_free + 8 * sr, ((ks - 1) / kStages) & 1);
-                issue_tma(kr);
-            }
-        }
-    }
-
-    // ---- epilogue: TMEM -> registers -> cost formula -> HBM -----------------------------------------
-    mbar_wait(bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-    const int x = x0 + warp * 32 + lane;                       // warp w owns TMEM lanes [32w, 32w + 32)
-    const float nx = x < job.s0 ? job.n0[x] : 1.0f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < kTN; c0 += 32) {
-        float dot[32];
-#pragma unroll
-        for (int acc = 0; acc < 3; ++acc) {
-            if (acc == 1 && nk < 2) continue;                 // odd-slice accumulator never written
-            uint32_t r[32];
-            const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16) + (unsigned)(acc * kTN + c0);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dot[j] = acc == 0 ? __uint_as_float(r[j]) : __fadd_rn(dot[j], __uint_as_float(r[j]));
-        }
-        if (x < job.s0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int y = y0 + c0 + j;
-                if (y < job.s1) {
-                    job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(dot[j], nx, job.n1[y]);
-                    if (job.dots) job.dots[(size_t)x * job.s1 + y] = dot[j];
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int j, x0, y0;
+                if (!tile_of(t, j, x0, y0)) continue;
+                const void *tm0 = jobs[j].tmap0, *tm1 = jobs[j].tmap1;
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(bar_free + 8 * s, ((it / kStages) & 1) ^ 1);
+                    const unsigned base = tiles_u32 + s * kStageBytes;
+                    mbar_expect_tx(bar_raw + 8 * s, 2 * kTileBytes);
+                    tma_load_2d(base, tm0, bar_raw + 8 * s, ks * kTK, x0);
+                    tma_load_2d(base + kTileBytes, tm1, bar_raw + 8 * s, ks * kTK, y0);
                 }
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int it = 0, nt = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                int j, x0, y0;
+                if (!tile_of(t, j, x0, y0)) continue;
+                mbar_wait(bar_drained, (nt & 1) ^ 1);                    // the previous tile's epilogue has read the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+                for (int ks = 0; ks < nk; ++ks, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(bar_split + 8 * s, (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+                    const unsigned base = tiles_u32 + s * kStageBytes;
+                    const unsigned a_hi = base, b_hi = base + kTileBytes, a_lo = base + 2 * kTileBytes, b_lo = base + 3 * kTileBytes;
+                    // The tensor core rounds toward zero each time it adds an MMA result into the fp32
+                    // accumulator, so the error grows with the number of MMAs per accumulator.  The hi.hi
+                    // products alternate between two accumulators (even / odd k-slices) and the two small
+                    // cross terms (2^-11 of the main term) go to a third one; the epilogue adds the three.
+                    const unsigned d_main = tmem_d + (unsigned)((ks & 1) * kTN);
+                    const unsigned d_cross = tmem_d + (unsigned)(2 * kTN);
+#pragma unroll
+                    for (int k = 0; k < kTK / 8; ++k) {                // UMMA K = 8 tf32 = 32 bytes along the row
+                        const unsigned off = k * 32;
+                        umma_tf32(d_main, umma_desc(a_hi + off), umma_desc(b_hi + off), (ks >= 2) || k != 0);
+                        umma_tf32(d_cross, umma_desc(a_hi + off), umma_desc(b_lo + off), (ks | k) != 0);
+                        umma_tf32(d_cross, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+                    }
+                    umma_commit(bar_free + 8 * s);                     // arrives when these MMAs have read the stage
+                }
+                umma_commit(bar_acc);
+                ++nt;
+            }
+        }
+    } else {
+        // ---- splitters + epilogue: threads 64..191, et = 0..127; TMEM lanes [32 (warp % 4), +32) belong to this warp ----
+        const int et = tid - 64, quarter = warp & 3;
+        int it = 0, nt = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            int j, x0, y0;
+            if (!tile_of(t, j, x0, y0)) continue;
+            const SvxDenseJob &job = jobs[j];
+            for (int ks = 0; ks < nk; ++ks, ++it) {
+                const int s = it % kStages;
+                mbar_wait(bar_raw + 8 * s, (it / kStages) & 1);          // both operand slices have landed
+                // hi/lo split, elementwise: the swizzled position of an element is the same in all four tiles
+                float4 *hi4 = reinterpret_cast<float4 *>(tiles + (size_t)s * kStageBytes);
+                float4 *lo4 = hi4 + 2 * kTileBytes / 16;
+#pragma unroll 4
+                for (int i = et; i < 2 * kTileBytes / 16; i += 128) {
+                    float4 v = hi4[i], lo;
+                    split_tf32(v, lo);
+                    hi4[i] = v;
+                    lo4[i] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_split + 8 * s);
+            }
+            // ---- epilogue: TMEM -> registers -> cost formula -> HBM ---------------------------------------------
+            mbar_wait(bar_acc, nt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            const int x = x0 + quarter * 32 + lane;
+            const float nx = x < job.s0 ? job.n0[x] : 1.0f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTN; c0 += 32) {
+                float dot[32];
+#pragma unroll
+                for (int acc = 0; acc < 3; ++acc) {
+                    if (acc == 1 && nk < 2) continue;                 // odd-slice accumulator never written
+                    uint32_t r[32];
+                    const unsigned taddr = tmem_d + ((unsigned)(quarter * 32) << 16) + (unsigned)(acc * kTN + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) dot[q] = acc == 0 ? __uint_as_float(r[q]) : __fadd_rn(dot[q], __uint_as_float(r[q]));
+                }
+                if (c0 + 32 >= kTN) {
+                    // every accumulator column has been read: the next tile's MMAs may overwrite them while the formula runs
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_drained);
+                }
+                if (x < job.s0) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const int y = y0 + c0 + q;
+                        if (y < job.s1) {
+                            job.costs[(size_t)x * job.s1 + y] = svx_dense_cost(dot[q], nx, job.n1[y]);
+                            if (job.dots) job.dots[(size_t)x * job.s1 + y] = dot[q];
+                        }
+                    }
+                }
+            }
+            ++nt;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
     __syncthreads();
-    if (warp == 0)
+    if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols));
 }
 
@@ -291,9 +343,16 @@ int svx_dense_costs_tc_launch(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs
             if (jb.s0 > 0 && jb.s1 > 0) { m0 = jb.s0 > m0 ? jb.s0 : m0; m1 = jb.s1 > m1 ? jb.s1 : m1; }
         }
         if (m0 == 0 || m1 == 0) continue;
-        dim3 grid((m1 + kTN - 1) / kTN, (m0 + kTM - 1) / kTM, nj);
-        SVX_REQUIRE(grid.y <= 65535, SVX_ERR_UNSUPPORTED, "svx_dense_costs: s0 %d too large", m0);
-        k_dense_costs_tc<<<grid, 128, kSmemBytes, st>>>(jobs_d + j0, dim);
+        const int tx = (m1 + kTN - 1) / kTN, ty = (m0 + kTM - 1) / kTM;
+        const long long ntiles = (long long)tx * ty * nj;
+        static int sms = 0;
+        if (!sms) {
+            int devid = 0;
+            SVX_CUDA_OK(cudaGetDevice(&devid));
+            SVX_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid));
+        }
+        const int grid = (int)(ntiles < sms ? ntiles : sms);          // persistent: one CTA per SM walks the tile list
+        k_dense_costs_tc<<<grid, kTcThreads, kSmemBytes, st>>>(jobs_d + j0, dim, tx, ty, nj);
         SVX_LAUNCH_CHECK();
     }
     return SVX_OK;

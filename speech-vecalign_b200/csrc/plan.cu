@@ -580,6 +580,24 @@ extern "C" int svx_plan_upload(SvxPlan *pl, int stage_is_pinned, void *stream)
     return SVX_OK;
 }
 
+// The same reset from a DEVICE copy of the staging block (a caller that runs several plans in one arena keeps each
+// plan's host-initialised prefix in device memory and restores it before every run: no PCIe traffic per run).
+extern "C" int svx_plan_restore(SvxPlan *pl, const void *stage_copy_d, void *stream)
+{
+    SVX_REQUIRE(pl && pl->bound && (stage_copy_d || pl->R == 0), SVX_ERR_ARG, "svx_plan_restore: plan not bound / null copy");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl->R == 0) return SVX_OK;
+    const long long nn = (pl->norms_hi - pl->norms_lo) / 4;
+    if (nn > 0) {
+        const int blocks = (int)std::min<long long>((nn + 1023) / 1024, 148 * 8);
+        k_fill_f32<<<blocks, 256, 0, st>>>(reinterpret_cast<float *>(pl->arena + pl->norms_lo), nn, 1.0f);
+        SVX_LAUNCH_CHECK();
+    }
+    SVX_CUDA_OK(cudaMemsetAsync(pl->arena + pl->zero_lo, 0, (size_t)(pl->arena_bytes - pl->zero_lo), st));
+    SVX_CUDA_OK(cudaMemcpyAsync(pl->arena, stage_copy_d, (size_t)pl->host_bytes, cudaMemcpyDeviceToDevice, st));
+    return SVX_OK;
+}
+
 extern "C" int svx_plan_launcher_name(const SvxPlan *pl, int i, char *buf, int cap)
 {
     SVX_REQUIRE(pl && buf && i >= 0 && i < (int)pl->chain.size(), SVX_ERR_ARG, "svx_plan_launcher_name: bad index");

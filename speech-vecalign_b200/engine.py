@@ -234,7 +234,19 @@ class BatchRun:
     def upload(self):
         """Staging block -> arena on the current stream (descriptors, draws, default penalties; norms preset to 1.0,
         status cleared).  Needed again only when another batch has used the same arena in between."""
-        capi.check(capi.lib().svx_plan_upload(self.plan.handle, 1, torch.cuda.current_stream(self.dev).cuda_stream), "svx_plan_upload")
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self._init_copy is not None:
+            capi.check(capi.lib().svx_plan_restore(self.plan.handle, self._init_copy.data_ptr(), stream), "svx_plan_restore")
+        else:
+            capi.check(capi.lib().svx_plan_upload(self.plan.handle, 1, stream), "svx_plan_upload")
+
+    _init_copy = None
+
+    def keep_init_on_device(self):
+        """Keeps a device copy of the staging block: later upload() calls restore the arena's host-initialised prefix
+        from it (several batches taking turns in one arena, bench.py's config-4 corpus) instead of crossing PCIe."""
+        self._init_copy = torch.empty(max(self.host_init_bytes, 16), dtype=torch.uint8, device=self.dev)
+        self._init_copy.copy_(self._stage[:self._init_copy.numel()], non_blocking=True)
 
     @property
     def knob(self):
