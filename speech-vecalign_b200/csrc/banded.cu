@@ -1163,8 +1163,13 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
         static const char *which = getenv("SVX_COSTS_KERNEL") ? getenv("SVX_COSTS_KERNEL") : "p2";
         static const bool per_cell = (getenv("SVX_COSTS_CELL") && atoi(getenv("SVX_COSTS_CELL")) != 0) || !strcmp(which, "cell");
         static const bool use_p2 = !per_cell && !strcmp(which, "p2");
-        static const int p2_bc = getenv("SVX_P2_BC") ? atoi(getenv("SVX_P2_BC")) : 16;
-        static const int p2_stages = getenv("SVX_P2_STAGES") ? atoi(getenv("SVX_P2_STAGES")) : 4;
+        // slice width: 32 floats for K <= 4 (measured 13.6 vs 14.3 ms on config 2), 16 above (a 32-float stage of
+        // K >= 5 rows leaves room for two stages only); three ring stages - a fourth one was SLOWER at K = 7
+        // (42.6 vs 35.0 ms on config 5: the larger shared-memory carve-out leaves the L1 no room for the 4-byte copies)
+        static const int p2_bc_env = getenv("SVX_P2_BC") ? atoi(getenv("SVX_P2_BC")) : 0;
+        static const int p2_stages_env = getenv("SVX_P2_STAGES") ? atoi(getenv("SVX_P2_STAGES")) : 0;
+        const int p2_bc = p2_bc_env ? p2_bc_env : (K <= 4 ? 32 : 16);
+        const int p2_stages = p2_stages_env ? p2_stages_env : 3;
         static const int p2_prod = getenv("SVX_P2_PRODUCERS") ? atoi(getenv("SVX_P2_PRODUCERS")) : 4;   // clamped to 12 warps per CTA
         static const int p2_mink = getenv("SVX_P2_MINK") ? atoi(getenv("SVX_P2_MINK")) : 2;   // K = 1 (coarse levels, one type) is copy-bound
         if (standard && use_p2 && K >= p2_mink && K <= 7)

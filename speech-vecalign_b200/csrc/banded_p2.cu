@@ -17,11 +17,11 @@
 // and it occupies the FP32 pipe for two cycles per issue: the exact stream needs 1 issue slot per MAC
 // instead of 2, which is what bounded the scalar kernel (issue-active 82 %, FMA pipe 67 %).
 //
-// Tile = 32 consecutive block-diagonals of one job (65 anti-diagonals, the first and last shared with the
-// neighbouring tiles cell by cell - every band cell belongs to exactly one block, so to exactly one tile).
-// Warp = one band slot (Y - Ymin(e)), lane = block-diagonal: B/2 + 1 warps cover every band cell (proved by
-// enumeration in tests/test_host_logic.py), every lane of every warp owns a block, and the eight lanes of an
-// LDS.128 phase read rows that are equal or consecutive (X and Y advance by 0 or 1 along e): no conflicts.
+// Tile = ne = 256 / (B/2 + 1) consecutive block-diagonals of one job (2 ne + 1 anti-diagonals, the first and last shared
+// with the neighbouring tiles cell by cell - every band cell belongs to exactly one block, so to exactly one tile).
+// B/2 + 1 band slots (Y - Ymin(e)) cover every band cell of a block-diagonal (proved by enumeration in
+// tests/test_host_logic.py); the 256 consumer threads own the (block-diagonal, slot) pairs slot-fastest, so the eight
+// lanes of an LDS.128 phase read consecutive rows (consecutive Y, descending X): no conflicts inside a block-diagonal.
 // Shared-memory layout of one embedding slice (BC floats): x rows as PAIR ROWS, the two positions of a block
 // interleaved float by float ({x[2X][d], x[2X+1][d]} is then one aligned 8-byte word = one FFMA2 operand),
 // staged with 4-byte cp.async; y rows as [even positions | odd positions], 16-byte cp.async; both through a
@@ -58,7 +58,7 @@ __device__ __forceinline__ u64 mac2(u64 acc, u64 x2, float y, u64 one2, u64 nz2)
     return fma2(x2, y2, acc);
 }
 
-constexpr int kNE = 32;                 // block-diagonals per tile = lanes
+constexpr int kConsWarps = 8;            // consumer warps per CTA: two per scheduler, whatever the band width
 
 __device__ __forceinline__ void mbar_init(unsigned bar, int count)
 {
@@ -87,14 +87,14 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 }
 
 // K: overlaps per side; BC: floats of the embedding dimension per staged slice; DV: floats per operand load.
-// Warps [0, nb) are consumers (nb = band / 2 + 1 band slots), the remaining 1-2 warps are producers: they move
+// Warps [0, 8) are consumers, the remaining 1-4 warps are producers: they move
 // slice after slice of the tile's rows into a ring of `nstages` buffers with cp.async and signal each buffer's
 // `full` mbarrier (cp.async.mbarrier.arrive); a consumer warp waits for `full`, multiplies, and arrives on the
 // buffer's `empty` mbarrier.  No CTA-wide barrier in the slice loop: the consumer warps drift apart by up to the
 // ring depth, and the copy address arithmetic stays off the consumers' FP32 pipe (IMAD shares it with FFMA2).
 template <int K, int BC, int DV, bool EXACT>
 __global__ void __launch_bounds__(svx_p2_max_threads(K), 1)
-k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float one, float nz)
+k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, float one, float nz)
 {
     constexpr int T = K * (K + 1) / 2;
     constexpr int XS = 2 * BC + 4;      // pair-row stride in floats: 8 consecutive pair rows tile the 32 banks
@@ -103,15 +103,15 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float on
     extern __shared__ __align__(16) float tile[];
     const SvxBandJob &job = jobs[blockIdx.y];
     const int A = job.a_len;
-    const int e_first = kNE * (int)blockIdx.x - 1;           // e = -1 holds the (odd, odd) cells of diagonal 0
-    const int d_first = max(2 * e_first, 0), d_last = min(2 * (e_first + kNE - 1) + 2, A - 1);
+    const int e_first = ne * (int)blockIdx.x - 1;            // e = -1 holds the (odd, odd) cells of diagonal 0
+    const int d_first = max(2 * e_first, 0), d_last = min(2 * (e_first + ne - 1) + 2, A - 1);
     if (d_first > d_last) return;
     const int B = job.band, w = job.width_over2;
     const int s0 = job.s0, s1 = job.s1;
     const int32_t *ypath = job.ypath;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nprod = (nthreads >> 5) - nb;
+    const int nprod = (nthreads >> 5) - kConsWarps;
 
     // positions touched by the tile, rounded out to whole blocks.  The search path is monotone (x or y advances
     // by one per anti-diagonal), so the first / last diagonal bound every band offset of the tile.
@@ -119,85 +119,99 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float on
     const int ylo = (bf >> 1) * 2, yhi = ((bl + B - 1) >> 1) * 2 + 1;
     const int xlo = ((d_first - (bf + B - 1)) >> 1) * 2, xhi = ((d_last - bl) >> 1) * 2 + 1;
     const int NX = xhi - xlo + 1, NY = yhi - ylo + 1, HX = NX >> 1, HY = NY >> 1;
-    const int rows_cap = svx_p2_rows_cap(B);
+    const int rows_cap = svx_p2_rows_cap(B, ne);
     if (NX <= 0 || NY <= 0 || NX + NY > rows_cap) return;    // not a search path (an earlier level failed: status_d says so)
     const int stage_floats = K * rows_cap * YS;
-    // after the ring: per staged row {source float offset from v0 / v1 (-1: zero row), byte offset in a stage};
+    // after the ring: the copy lists - one entry {source float offset from v0 / v1, byte offset in a stage} per staged row
+    // that HAS a source row; rows outside the documents / overlaps are zeroed once in every stage and never copied -
     // then the mbarriers
-    int2 *rowtab = reinterpret_cast<int2 *>(tile + (size_t)nstages * stage_floats);
-    const unsigned bars = (unsigned)__cvta_generic_to_shared(rowtab + K * rows_cap);     // full[nstages], empty[nstages]
+    int2 *xlist = reinterpret_cast<int2 *>(tile + (size_t)nstages * stage_floats);
+    int2 *ylist = xlist + K * rows_cap;
+    int *counts = reinterpret_cast<int *>(ylist + K * rows_cap);                          // [0] x rows, [1] y rows
+    const unsigned bars = (unsigned)__cvta_generic_to_shared(counts + 2);                 // full[nstages], empty[nstages]
     const int xstride = HX * XS;       // floats between overlaps in the x region
     const int ystride = NY * YS;
     const int ybase = K * HX * XS;     // the y region follows the x region
+    if (tid < 2) counts[tid] = 0;
+    if (tid < 2 * nstages) mbar_init(bars + 8 * tid, tid < nstages ? 32 * nprod : kConsWarps);
+    __syncthreads();
 
     // x: slot k * NX + p is position xlo + p of overlap k, written into pair row p / 2 at float 2 d + (p & 1);
     // y: slot K * NX + k * NY + q is position ylo + 2 q (q < HY) or ylo + 2 (q - HY) + 1 of overlap k
     const int xrows = K * NX, yrows = K * NY;
     for (int r = tid; r < xrows + yrows; r += nthreads) {
         int off = -1, dst;
-        if (r < xrows) {
+        const bool isx = r < xrows;
+        if (isx) {
             const int k = r / NX, p = r - k * NX, seg = xlo + p;
             if (k < job.k0 && seg >= 0 && seg < s0) off = (int)(((size_t)k * s0 + seg) * dim);
-            dst = (k * xstride + (p >> 1) * XS + (p & 1)) * (int)sizeof(float);
+            dst = k * xstride + (p >> 1) * XS + (p & 1);
         } else {
             const int r2 = r - xrows;
             const int k = r2 / NY, q = r2 - k * NY;
             const int seg = ylo + (q < HY ? 2 * q : 2 * (q - HY) + 1);
             if (k < job.k1 && seg >= 0 && seg < s1) off = (int)(((size_t)k * s1 + seg) * dim);
-            dst = (ybase + r2 * YS) * (int)sizeof(float);
+            dst = ybase + r2 * YS;
         }
-        rowtab[r] = make_int2(off, dst);
+        if (off >= 0) {
+            const int slot = atomicAdd(&counts[isx ? 0 : 1], 1);
+            (isx ? xlist : ylist)[slot] = make_int2(off, dst * (int)sizeof(float));
+        } else {
+            for (int st = 0; st < nstages; ++st)
+                for (int d = 0; d < BC; ++d) tile[(size_t)st * stage_floats + dst + (isx ? 2 * d : d)] = 0.0f;
+        }
     }
-    if (tid < 2 * nstages) mbar_init(bars + 8 * tid, tid < nstages ? 32 * nprod : nb);
     __syncthreads();
     const unsigned tile_u32 = (unsigned)__cvta_generic_to_shared(tile);
     const int slices = dim / BC;
 
-    if (warp >= nb) {
-        // ---- producers ----------------------------------------------------------------------------------------
-        const int pw = warp - nb;
+    if (warp >= kConsWarps) {
+        // ---- producers: lane = position inside a row slice, sub-rows of a warp instruction = consecutive list entries --------
+        const int pw = warp - kConsWarps;
         const char *gx = reinterpret_cast<const char *>(job.v0), *gy = reinterpret_cast<const char *>(job.v1);
         constexpr int XR = 32 / BC;            // x rows per warp instruction (4-byte copies, lane = d)
         constexpr int YR = 32 / (BC / 4);      // y rows per warp instruction (16-byte copies)
+        constexpr int UB = 8;                  // list entries fetched before their copies are issued
         const int xd = lane % BC, xsub = lane / BC;
         const int yc = lane % (BC / 4), ysub = lane / (BC / 4);
+        const int nx = counts[0], ny = counts[1];
+        const int xstep = nprod * XR, ystep = nprod * YR;
         for (int sl = 0; sl < slices; ++sl) {
             const int s = sl % nstages;
             if (sl >= nstages) mbar_wait(bars + 8 * (nstages + s), (unsigned)((sl / nstages - 1) & 1));
             const unsigned buf = tile_u32 + (unsigned)(s * stage_floats * (int)sizeof(float));
-            // eight table entries are fetched before the eight copies they describe are issued: one shared-memory
-            // latency per batch instead of one per copy
-            constexpr int UB = 8;
-            const unsigned xdst = buf + (unsigned)(8 * xd);
-            const long long xsrc = (long long)(sl * BC + xd) * 4;
-            for (int r0 = pw * XR + xsub; r0 < xrows; r0 += UB * nprod * XR) {
-                int2 ent[UB];
+            {
+                const unsigned dst0 = buf + (unsigned)(8 * xd);
+                const char *src0 = gx + (size_t)(sl * BC + xd) * 4;
+                int i = pw * XR + xsub;
+                for (; i + (UB - 1) * xstep < nx; i += UB * xstep) {
+                    int2 ent[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int r = r0 + u * nprod * XR;
-                    ent[u] = r < xrows ? rowtab[r] : make_int2(-2, 0);
+                    for (int u = 0; u < UB; ++u) ent[u] = xlist[i + u * xstep];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst0 + (unsigned)ent[u].y), "l"(src0 + (long long)ent[u].x * 4));
                 }
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    if (ent[u].x == -2) continue;
-                    const char *gp = gx + (ent[u].x < 0 ? 0ll : (long long)ent[u].x * 4 + xsrc);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(xdst + (unsigned)ent[u].y), "l"(gp), "r"(ent[u].x < 0 ? 0 : 4));
+                for (; i < nx; i += xstep) {
+                    const int2 e = xlist[i];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst0 + (unsigned)e.y), "l"(src0 + (long long)e.x * 4));
                 }
             }
-            const unsigned ydst = buf + (unsigned)(16 * yc);
-            const long long ysrc = (long long)(sl * BC + 4 * yc) * 4;
-            for (int r0 = pw * YR + ysub; r0 < yrows; r0 += UB * nprod * YR) {
-                int2 ent[UB];
+            {
+                const unsigned dst0 = buf + (unsigned)(16 * yc);
+                const char *src0 = gy + (size_t)(sl * BC + 4 * yc) * 4;
+                int i = pw * YR + ysub;
+                for (; i + (UB - 1) * ystep < ny; i += UB * ystep) {
+                    int2 ent[UB];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    const int r = r0 + u * nprod * YR;
-                    ent[u] = r < yrows ? rowtab[xrows + r] : make_int2(-2, 0);
+                    for (int u = 0; u < UB; ++u) ent[u] = ylist[i + u * ystep];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + (unsigned)ent[u].y), "l"(src0 + (long long)ent[u].x * 4));
                 }
-#pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    if (ent[u].x == -2) continue;
-                    const char *gp = gy + (ent[u].x < 0 ? 0ll : (long long)ent[u].x * 4 + ysrc);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(ydst + (unsigned)ent[u].y), "l"(gp), "r"(ent[u].x < 0 ? 0 : 16));
+                for (; i < ny; i += ystep) {
+                    const int2 e = ylist[i];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst0 + (unsigned)e.y), "l"(src0 + (long long)e.x * 4));
                 }
             }
             mbar_arrive_cp_async(bars + 8 * s);
@@ -207,10 +221,15 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float on
     }
 
     // ---- consumers: this thread's block ----------------------------------------------------------------------
-    const int yi = warp;
-    const int e = e_first + lane;
+    // The 256 consumer threads take the tile's (block-diagonal, band slot) pairs slot-fastest: thread t owns slot t % nb of
+    // block-diagonal e_first + t / nb, ne = 256 / nb block-diagonals per tile.  Every scheduler then runs two consumer
+    // warps whatever the band width (a warp per slot gave 9 or 10 warps at bands 16 / 18: 3 + 2 + 2 + 2 per scheduler),
+    // and the eight lanes of an LDS.128 phase read consecutive rows (consecutive slots = consecutive Y, descending X).
+    const int ei = tid / nb, yi = tid - ei * nb;
+    const int e = e_first + ei;
+    const bool in_tile = ei < ne;
     const int dA = 2 * e, dB = 2 * e + 1, dC = 2 * e + 2;
-    const bool vA = dA >= 0 && dA < A, vB = dB >= 0 && dB < A, vC = dC >= 0 && dC < A;
+    const bool vA = in_tile && dA >= 0 && dA < A, vB = in_tile && dB >= 0 && dB < A, vC = in_tile && dC >= 0 && dC < A;
     const int bA = vA ? ypath[dA] - w : 0, bB = vB ? ypath[dB] - w : 0, bC = vC ? ypath[dC] - w : 0;
     // smallest Y with a band cell on one of the three diagonals: even yy on dA, both parities on dB, odd yy on dC
     int ymin = INT_MAX;
@@ -318,26 +337,29 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, float on
 template <int K, int BC, int DV>
 int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, int nstages, int nprod, cudaStream_t st)
 {
-    const int nb = band / 2 + 1;
+    const int nb = band / 2 + 1;                                   // band slots (2 x 2 blocks) per block-diagonal
+    if (nb > 32 * kConsWarps) return -1;
+    int ne = 32 * kConsWarps / nb;                                 // block-diagonals per tile
+    if (ne > 40) ne = 40;
     if (nprod < 1) nprod = 1;
-    while (nprod > 1 && 32 * (nb + nprod) > svx_p2_max_threads(K)) --nprod;
-    const int threads = 32 * (nb + nprod);
-    const int rows_cap = svx_p2_rows_cap(band);
+    if (nprod > 4) nprod = 4;
+    const int threads = 32 * (kConsWarps + nprod);
+    const int rows_cap = svx_p2_rows_cap(band, ne);
     const size_t stage_bytes = (size_t)K * rows_cap * (BC + 4) * sizeof(float);
-    const size_t table = (size_t)K * rows_cap * sizeof(int2) + 2 * 8 * 8;
+    const size_t table = (size_t)2 * K * rows_cap * sizeof(int2) + 16 + 2 * 8 * 8;
     while (nstages > 2 && nstages * stage_bytes + table > 225 * 1024) --nstages;
     const size_t smem = nstages * stage_bytes + table;
     if (threads > svx_p2_max_threads(K) || smem > 225 * 1024 || dim % BC) return -1;
     const int emax = (max_alen - 1) >> 1;                          // block-diagonals -1 .. emax
-    dim3 grid((emax + 2 + kNE - 1) / kNE, nj);
+    dim3 grid((emax + 2 + ne - 1) / ne, nj);
     if (mode == SVX_COST_EXACT) {
         auto kern = k_banded_costs_p2<K, BC, DV, true>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, 1.0f, -0.0f);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
     } else {
         auto kern = k_banded_costs_p2<K, BC, DV, false>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, 1.0f, -0.0f);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
     }
     SVX_LAUNCH_CHECK();
     return SVX_OK;

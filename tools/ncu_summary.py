@@ -19,6 +19,7 @@ LAUNCHER = [  # kernel-name prefix -> bench.py launcher name
     ("k_center", "svx_downsample"), ("k_sample_mean", "svx_sample_norms"), ("k_norms_gemv", "svx_sample_norms"),
     ("k_sort_samples", "svx_score_pairs"), ("k_score_pairs", "svx_score_pairs"), ("k_del_knob", "svx_del_knob"),
     ("k_dense_costs", "svx_dense_costs"), ("k_dense_dp", "svx_dense_dp"), ("k_upload", "svx_upload_pinned"),
+    ("k_fill_f32", "svx_plan_upload"), ("k_margin", "svx_margin_scores"), ("k_gather", "svx_gather_doc_embedding"),
 ]
 
 
