@@ -122,7 +122,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_dense_costs_tc(const SvxDense
     __shared__ __align__(8) unsigned long long bars[3 * kStages + 2];   // raw[], split[], free[], accumulators done, accumulators drained
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B atoms) by an OFFSET into the dynamic shared array: rounding the pointer through
+    // uintptr_t made it a generic pointer, and the hi / lo split then ran on generic LD / ST (ncu: long-scoreboard
+    // stalls on every split instruction, 2.2 us per k-slice) instead of LDS / STS
+    unsigned char *tiles = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const unsigned tiles_u32 = smem_u32(tiles);
     const unsigned bar_raw = smem_u32(&bars[0]), bar_split = smem_u32(&bars[kStages]), bar_free = smem_u32(&bars[2 * kStages]);
     const unsigned bar_acc = smem_u32(&bars[3 * kStages]), bar_drained = smem_u32(&bars[3 * kStages + 1]);
