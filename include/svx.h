@@ -320,7 +320,9 @@ typedef struct SvxPlanInfo {
     int64_t ndraw_calls;
     int64_t arena_bytes;           /* device workspace                                          */
     int64_t host_bytes;            /* staging block = the host-initialised prefix of the arena  */
-    int64_t result_offset;         /* [result_offset, arena_bytes): records, counts, status     */
+    int64_t result_offset;         /* [result_offset, +result_bytes): the level-0 alignment records */
+    int64_t result_bytes;
+    int64_t counts_offset;         /* [counts_offset, arena_bytes): record counts and status words  */
     double fallback_del_penalty;   /* dp_utils.py:315-321                                       */
 } SvxPlanInfo;
 

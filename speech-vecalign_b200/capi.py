@@ -61,7 +61,8 @@ PARAMS = np.dtype([("k0", np.int32), ("k1", np.int32), ("dim", np.int32), ("ntyp
 PLAN_INFO = np.dtype([("npairs", np.int32), ("nrecords", np.int32), ("max_depth", np.int32), ("band", np.int32),
                       ("width_over2", np.int32), ("per0", np.int32), ("per1", np.int32), ("fused_prologue", np.int32),
                       ("nlaunchers", np.int32), ("ndraw_calls", np.int64), ("arena_bytes", np.int64), ("host_bytes", np.int64),
-                      ("result_offset", np.int64), ("fallback_del_penalty", np.float64)], align=True)
+                      ("result_offset", np.int64), ("result_bytes", np.int64), ("counts_offset", np.int64),
+                      ("fallback_del_penalty", np.float64)], align=True)
 
 _STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER, PARAMS, PLAN_INFO]
 

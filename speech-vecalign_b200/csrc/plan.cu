@@ -50,6 +50,7 @@ struct SvxPlan {
     std::vector<int64_t> rec_pair, rec_level, rs0, rs1, A, T, banded, rec_cap, nsamp, has_draw, is_top, top_rec, tgt_rec;
     std::vector<int64_t> off[SVX_PO_COUNT];
     int64_t host_bytes = 0, arena_bytes = 0, norms_lo = 0, norms_hi = 0, zero_lo = 0, jobs_off = 0, jobs_cap = 0;
+    int64_t result_lo = 0, result_hi = 0;          // level-0 alignment records
     std::vector<int64_t> draw_pair, draw_high, draw_count, draw_off, draw_begin;
     std::vector<JobArr> arrays;
     std::vector<Launcher> chain;
@@ -226,7 +227,18 @@ extern "C" int svx_plan_create(const SvxAlignParams *prm, int npairs, const int3
     lay(SVX_PO_BCOST, [&](int64_t r) { return pl->A[r] * pl->T[r] * band * 4; });
     lay(SVX_PO_BBP, [&](int64_t r) { return pl->banded[r] ? (pl->A[r] + 2) * band : 0; });
     lay(SVX_PO_BCSUM, [&](int64_t r) { return pl->banded[r] ? (pl->A[r] + 2) * band * 8 : 0; });
-    lay(SVX_PO_RECS, [&](int64_t r) { return pl->rec_cap[r] * (int64_t)sizeof(SvxAlignRec); });
+    // alignment records: the level-0 ones (the results) first and contiguous, so that reading the results back moves
+    // only them; the coarser levels' records (consumed on the device by the next level's path builder) follow
+    pl->off[SVX_PO_RECS].assign(R, 0);
+    pl->result_lo = top;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t r = 0; r < R; ++r)
+            if ((rl[r] == 0) == (pass == 0)) {
+                pl->off[SVX_PO_RECS][r] = top;
+                top += (pl->rec_cap[r] * (int64_t)sizeof(SvxAlignRec) + kAlign - 1) / kAlign * kAlign;
+            }
+        if (pass == 0) pl->result_hi = top;
+    }
     pl->zero_lo = top;
     lay(SVX_PO_NRECS, [&](int64_t) { return (int64_t)4; });
     lay(SVX_PO_STATUS, [&](int64_t) { return (int64_t)8; });       // [0] banded status, [1] dense status
@@ -270,7 +282,9 @@ extern "C" int svx_plan_info(const SvxPlan *pl, SvxPlanInfo *info)
     info->nlaunchers = (int32_t)pl->chain.size();
     info->ndraw_calls = (int64_t)pl->draw_pair.size();
     info->arena_bytes = pl->arena_bytes; info->host_bytes = pl->host_bytes;
-    info->result_offset = pl->R ? pl->off[SVX_PO_RECS][0] : pl->arena_bytes;
+    info->result_offset = pl->result_lo;
+    info->result_bytes = pl->result_hi - pl->result_lo;
+    info->counts_offset = pl->zero_lo;
     info->fallback_del_penalty = pl->fallback_pen;
     return SVX_OK;
 }
@@ -652,21 +666,24 @@ extern "C" int svx_plan_fetch(const SvxPlan *pl, SvxAlignRec *recs_out, const in
     SVX_REQUIRE(pl && pl->bound, SVX_ERR_ARG, "svx_plan_fetch: plan not bound");
     if (pl->P == 0) return SVX_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t lo = pl->off[SVX_PO_RECS][0], n = pl->arena_bytes - lo;
-    std::vector<unsigned char> blob((size_t)n);
+    // three copies: the level-0 records, the record counts + status words, the penalties
+    const int64_t lo = pl->result_lo, n = pl->result_hi - pl->result_lo;
+    const int64_t clo = pl->zero_lo, cn = pl->arena_bytes - pl->zero_lo;
+    std::vector<unsigned char> blob((size_t)std::max<int64_t>(n, 1)), cnt((size_t)std::max<int64_t>(cn, 1));
     std::vector<unsigned char> pens((size_t)pl->R * kAlign);
     const int64_t plo = pl->off[SVX_PO_DELPEN][0];
-    SVX_CUDA_OK(cudaMemcpyAsync(blob.data(), pl->arena + lo, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (n > 0) SVX_CUDA_OK(cudaMemcpyAsync(blob.data(), pl->arena + lo, (size_t)n, cudaMemcpyDeviceToHost, st));
+    SVX_CUDA_OK(cudaMemcpyAsync(cnt.data(), pl->arena + clo, (size_t)cn, cudaMemcpyDeviceToHost, st));
     SVX_CUDA_OK(cudaMemcpyAsync(pens.data(), pl->arena + plo, pens.size(), cudaMemcpyDeviceToHost, st));
     SVX_CUDA_OK(cudaStreamSynchronize(st));
     for (int p = 0; p < pl->P; ++p) {
         const int64_t r0 = pl->first[p];
         const int64_t cap = pl->rec_cap[r0];
         int32_t nrec = 0, status = 0;
-        memcpy(&nrec, blob.data() + pl->off[SVX_PO_NRECS][r0] - lo, 4);
+        memcpy(&nrec, cnt.data() + pl->off[SVX_PO_NRECS][r0] - clo, 4);
         for (int64_t r = r0; r < r0 + pl->nlev[p]; ++r) {
             int32_t s2[2];
-            memcpy(s2, blob.data() + pl->off[SVX_PO_STATUS][r] - lo, 8);
+            memcpy(s2, cnt.data() + pl->off[SVX_PO_STATUS][r] - clo, 8);
             status |= s2[0] | s2[1];
         }
         const int64_t valid = std::min<int64_t>(nrec, cap);

@@ -252,7 +252,14 @@ def _vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_ove
         total_bytes = sum(4 * (sh0[0] * sh0[1] + sh1[0] * sh1[1]) * sh0[2] for (sh0, _), (sh1, _) in metas)
         cap = int(os.environ.get("SVX_PIPE_CHUNKS", "8"))
         nchunks = max(1, min(cap, P // 4, int(total_bytes * cap // (4096 << 20))))
-    bounds = [P * i // nchunks for i in range(nchunks + 1)]
+    # equal chunks except the last two (3/4 and 1/2 of a chunk): what is left to compute after the last copy has landed
+    # is the tail of the timeline
+    wts = [1.0] * nchunks
+    if nchunks >= 4:
+        wts[-2], wts[-1] = 0.75, 0.5
+    acc_w = np.concatenate([[0.0], np.cumsum(wts)]) / sum(wts)
+    bounds = [int(round(P * a)) for a in acc_w]
+    bounds[-1] = P
     cur = torch.cuda.current_stream(dev)
     piped = nchunks > 1
     copy_stream = _side_stream(dev, "copy") if piped else cur
@@ -309,6 +316,8 @@ def _vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_ove
             if _tr and piped:
                 e_a = torch.cuda.Event(enable_timing=True); e_a.record(st)
             run.run(ngroups=1 if piped else ngroups)
+            if sync and not debug:
+                run.start_fetch()          # results of this chunk travel while the next chunks run
             if _tr and piped:
                 e_b = torch.cuda.Event(enable_timing=True); e_b.record(st); _ev.append((c, e_a, e_b))
             _mark(f"chunk {c} enqueued")

@@ -390,30 +390,51 @@ class BatchRun:
         top = self.rec_level == self.depth[self.rec_pair]
         return int(((self.A[self.banded] + 2) * self.band).sum() + ((self.rs0[top] + 1) * (self.rs1[top] + 1)).sum())
 
+    def start_fetch(self):
+        """Queues the device -> host copies of the results on the current stream, into pinned buffers: the level-0
+        alignment records, the record counts + status words, the penalties.  results() waits for them; calling this right
+        after run() lets the copies of one batch overlap the kernels of the next."""
+        info = self.plan.info
+        lo, n = int(info["result_offset"]), int(info["result_bytes"])
+        clo = int(info["counts_offset"])
+        dp_lo = int(self.off["delpen"].min()) if self.R else 0
+        spans = [(lo, n), (clo, self.nbytes - clo), (dp_lo, self.R * _ALIGN)]
+        bufs = []
+        for off, nb in spans:
+            h = torch.empty(max(nb, 1), dtype=torch.uint8, pin_memory=True)
+            if nb > 0:
+                h[:nb].copy_(self.arena[off:off + nb], non_blocking=True)
+            bufs.append(h)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._fetch = (bufs, ev, lo, clo, dp_lo)
+
+    _fetch = None
+
     def results(self):
-        """Device -> host read of the level-0 alignment records, scores, penalties and status.
+        """Level-0 alignment records, scores, penalties and status of every pair (device -> host).
         Returns a list (one per pair) of dicts with 'recs' (structured array, forward order),
         'del_penalty' (per level), 'status'."""
+        if self._fetch is None:
+            self.start_fetch()
+        (rb, cb, pb), ev, lo, clo, dp_lo = self._fetch
+        self._fetch = None
+        ev.synchronize()
+        blob, cnt, dp_blob = rb.numpy(), cb.numpy(), pb.numpy()
         o = self.off
-        lo = int(o["recs"].min()) if self.R else 0
-        blob = self.arena[lo:self.nbytes].cpu().numpy()
-        dp_lo = int(o["delpen"].min()) if self.R else 0
-        dp_blob = self.arena[dp_lo:dp_lo + self.R * _ALIGN].cpu().numpy()
         out = []
         for p in range(self.P):
             r0 = int(self.first[p])
             cap = int(self.rec_cap[r0])
-            n = int(blob[o["nrecs"][r0] - lo:o["nrecs"][r0] - lo + 4].view(np.int32)[0])
-            st = blob[o["status"][r0] - lo:o["status"][r0] - lo + 8].view(np.int32).copy()
-            top = int(self.top_rec[p])
-            st_dense = int(blob[o["status"][top] - lo + 4:o["status"][top] - lo + 8].view(np.int32)[0])
+            n = int(cnt[o["nrecs"][r0] - clo:o["nrecs"][r0] - clo + 4].view(np.int32)[0])
             recs = blob[o["recs"][r0] - lo:o["recs"][r0] - lo + cap * capi.REC.itemsize].view(capi.REC)
             recs = recs[cap - min(n, cap):cap].copy()
             pens = [float(dp_blob[o["delpen"][r] - dp_lo:o["delpen"][r] - dp_lo + 8].view(np.float64)[0])
                     for r in range(r0, r0 + int(self.nlev[p]))]
-            status = int(st[0]) | st_dense
-            for r in range(r0 + 1, r0 + int(self.nlev[p])):
-                status |= int(blob[o["status"][r] - lo:o["status"][r] - lo + 4].view(np.int32)[0])
+            status = 0
+            for r in range(r0, r0 + int(self.nlev[p])):
+                st = cnt[o["status"][r] - clo:o["status"][r] - clo + 8].view(np.int32)
+                status |= int(st[0]) | int(st[1])
             out.append({"recs": recs, "nrecs": n, "del_penalty": pens, "status": status})
         return out
 
