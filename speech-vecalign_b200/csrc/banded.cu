@@ -1170,10 +1170,14 @@ extern "C" int svx_banded_costs(const SvxBandJob *jobs_d, const SvxBandJob *jobs
         static const int p2_stages_env = getenv("SVX_P2_STAGES") ? atoi(getenv("SVX_P2_STAGES")) : 0;
         const int p2_bc = p2_bc_env ? p2_bc_env : (K <= 4 ? 32 : 16);
         const int p2_stages = p2_stages_env ? p2_stages_env : 3;
+        static const int p2_cw_env = getenv("SVX_P2_CONSUMERS") ? atoi(getenv("SVX_P2_CONSUMERS")) : 0;
+        // consumer warps: 12 (three per scheduler, 128 registers) where the accumulators allow it - K <= 4: measured
+        // 12.6 vs 13.6 ms on config 2 - else 8 (168 registers)
+        const int p2_cw = p2_cw_env ? p2_cw_env : (K <= 4 ? 12 : 8);
         static const int p2_prod = getenv("SVX_P2_PRODUCERS") ? atoi(getenv("SVX_P2_PRODUCERS")) : 4;   // clamped to 12 warps per CTA
         static const int p2_mink = getenv("SVX_P2_MINK") ? atoi(getenv("SVX_P2_MINK")) : 2;   // K = 1 (coarse levels, one type) is copy-bound
         if (standard && use_p2 && K >= p2_mink && K <= 7)
-            rc = svx_launch_costs_p2(K, jobs_d + jb0, nj, max_alen, j0.band, dim, mode, p2_bc, p2_stages, p2_prod, st);
+            rc = svx_launch_costs_p2(K, jobs_d + jb0, nj, max_alen, j0.band, dim, mode, p2_bc, p2_stages, p2_prod, p2_cw, st);
         // the scalar register-blocked kernel (round 1): K <= 4 only - at K = 5 its 60 accumulators per thread made
         // the thread-per-cell kernel faster
         if (rc == -1 && standard && !per_cell && K <= 4 && (j0.band & 1) == 0) {

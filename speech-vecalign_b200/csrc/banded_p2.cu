@@ -58,7 +58,6 @@ __device__ __forceinline__ u64 mac2(u64 acc, u64 x2, float y, u64 one2, u64 nz2)
     return fma2(x2, y2, acc);
 }
 
-constexpr int kConsWarps = 8;            // consumer warps per CTA: two per scheduler, whatever the band width
 
 __device__ __forceinline__ void mbar_init(unsigned bar, int count)
 {
@@ -92,8 +91,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 // `full` mbarrier (cp.async.mbarrier.arrive); a consumer warp waits for `full`, multiplies, and arrives on the
 // buffer's `empty` mbarrier.  No CTA-wide barrier in the slice loop: the consumer warps drift apart by up to the
 // ring depth, and the copy address arithmetic stays off the consumers' FP32 pipe (IMAD shares it with FFMA2).
-template <int K, int BC, int DV, bool EXACT>
-__global__ void __launch_bounds__(svx_p2_max_threads(K), 1)
+// CW consumer warps (8 = two per scheduler, 168 registers; 12 = three per scheduler, 128 registers: K <= 4 only - the third
+// warp covers the FFMA2 dependency stalls the other two leave open, ncu: "wait" + "math throttle" on every other sample)
+template <int K, int BC, int DV, bool EXACT, int CW>
+__global__ void __launch_bounds__(32 * (CW + 4), 1)
 k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, float one, float nz)
 {
     constexpr int T = K * (K + 1) / 2;
@@ -111,6 +112,7 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, 
     const int32_t *ypath = job.ypath;
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
+    constexpr int kConsWarps = CW;
     const int nprod = (nthreads >> 5) - kConsWarps;
 
     // positions touched by the tile, rounded out to whole blocks.  The search path is monotone (x or y advances
@@ -221,8 +223,8 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, 
     }
 
     // ---- consumers: this thread's block ----------------------------------------------------------------------
-    // The 256 consumer threads take the tile's (block-diagonal, band slot) pairs slot-fastest: thread t owns slot t % nb of
-    // block-diagonal e_first + t / nb, ne = 256 / nb block-diagonals per tile.  Every scheduler then runs two consumer
+    // The 32 CW consumer threads take the tile's (block-diagonal, band slot) pairs slot-fastest: thread t owns slot t % nb of
+    // block-diagonal e_first + t / nb, ne = 32 CW / nb block-diagonals per tile.  Every scheduler then runs CW / 4 consumer
     // warps whatever the band width (a warp per slot gave 9 or 10 warps at bands 16 / 18: 3 + 2 + 2 + 2 per scheduler),
     // and the eight lanes of an LDS.128 phase read consecutive rows (consecutive slots = consecutive Y, descending X).
     const int ei = tid / nb, yi = tid - ei * nb;
@@ -334,13 +336,14 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, 
     }
 }
 
-template <int K, int BC, int DV>
+template <int K, int BC, int DV, int CW>
 int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, int nstages, int nprod, cudaStream_t st)
 {
+    constexpr int kConsWarps = CW;
     const int nb = band / 2 + 1;                                   // band slots (2 x 2 blocks) per block-diagonal
     if (nb > 32 * kConsWarps) return -1;
     int ne = 32 * kConsWarps / nb;                                 // block-diagonals per tile
-    if (ne > 40) ne = 40;
+    if (ne > 5 * CW) ne = 5 * CW;
     if (nprod < 1) nprod = 1;
     if (nprod > 4) nprod = 4;
     const int threads = 32 * (kConsWarps + nprod);
@@ -349,15 +352,15 @@ int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int di
     const size_t table = (size_t)2 * K * rows_cap * sizeof(int2) + 16 + 2 * 8 * 8;
     while (nstages > 2 && nstages * stage_bytes + table > 225 * 1024) --nstages;
     const size_t smem = nstages * stage_bytes + table;
-    if (threads > svx_p2_max_threads(K) || smem > 225 * 1024 || dim % BC) return -1;
+    if (smem > 225 * 1024 || dim % BC) return -1;
     const int emax = (max_alen - 1) >> 1;                          // block-diagonals -1 .. emax
     dim3 grid((emax + 2 + ne - 1) / ne, nj);
     if (mode == SVX_COST_EXACT) {
-        auto kern = k_banded_costs_p2<K, BC, DV, true>;
+        auto kern = k_banded_costs_p2<K, BC, DV, true, CW>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
     } else {
-        auto kern = k_banded_costs_p2<K, BC, DV, false>;
+        auto kern = k_banded_costs_p2<K, BC, DV, false, CW>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
     }
@@ -368,22 +371,26 @@ int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int di
 }  // namespace
 
 int svx_launch_costs_p2(int K, const SvxBandJob *jobs_d, int nj, int max_alen, int band, int dim, int mode, int bc,
-                        int nstages, int nprod, void *stream)
+                        int nstages, int nprod, int cons_warps, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (band & 1) return -1;
     if (nstages < 2) nstages = 2;
     if (nstages > 8) nstages = 8;
-#define P2(KK, BCC, DVV) return launch_p2_t<KK, BCC, DVV>(jobs_d, nj, max_alen, band, dim, mode, nstages, nprod, st)
+#define P2(KK, BCC, DVV, CWW) return launch_p2_t<KK, BCC, DVV, CWW>(jobs_d, nj, max_alen, band, dim, mode, nstages, nprod, st)
+#define P2K(KK)                                                    \
+    if (cons_warps == 12) { if (bc == 32) P2(KK, 32, 4, 12); else P2(KK, 16, 4, 12); } \
+    else { if (bc == 32) P2(KK, 32, 4, 8); else P2(KK, 16, 4, 8); }
     switch (K) {
-        case 1: if (bc == 32) P2(1, 32, 4); else P2(1, 16, 4);
-        case 2: if (bc == 32) P2(2, 32, 4); else P2(2, 16, 4);
-        case 3: if (bc == 32) P2(3, 32, 4); else P2(3, 16, 4);
-        case 4: if (bc == 32) P2(4, 32, 4); else P2(4, 16, 4);
-        case 5: if (bc == 32) P2(5, 32, 4); else P2(5, 16, 4);
-        case 6: P2(6, 16, 2);
-        case 7: P2(7, 16, 2);
+        case 1: P2K(1)
+        case 2: P2K(2)
+        case 3: P2K(3)
+        case 4: P2K(4)
+        case 5: if (bc == 32) P2(5, 32, 4, 8); else P2(5, 16, 4, 8);
+        case 6: P2(6, 16, 2, 8);
+        case 7: P2(7, 16, 2, 8);
         default: return -1;
     }
+#undef P2K
 #undef P2
 }
