@@ -6,10 +6,13 @@ legs do, and there only as the checker or the timed CPU baseline.
 
 * ``dp_core_oracle.c`` / ``core.py``  — plain-C port of ``svecalign/vecalign/dp_core.pyx``.
 * ``vecalign_oracle.py``             — numpy port of ``svecalign/vecalign/dp_utils.py``.
+* ``margin_oracle.py``               — numpy port of ``svecalign/postprocess/score_align.py:118-161`` (exact flat search
+  in place of the faiss index; pinned to the margin scores the reference shipped for its example).
 * ``_ref/`` (git-ignored, built by ``make -C oracle ref``) — the reference's own Cython core
   compiled from ``/root/reference`` in place; ``ref_loader.py`` imports it (and, in the build
   container only, the reference's Python driver straight from ``/root/reference``).
 
-Parity status: PINNED — see ``tests/test_oracle_vs_reference.py`` (live comparison with the real
-reference in the build container) and ``tests/golden/`` (reference outputs committed for the GPU box).
+Parity status: PINNED — see ``tests/test_oracle_golden.py`` (live comparison with the real reference in the
+build container, the reference's compiled core wherever ``_ref`` travelled, and the committed fixtures) and
+``tests/golden/`` (reference outputs committed for the GPU box).
 """
