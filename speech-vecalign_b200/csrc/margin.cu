@@ -21,6 +21,7 @@
 //                     row, which keeps a sorted top-16 of  key = q.b - |b|^2 / 2  in registers across the whole sweep
 //                     (a value enters only if it beats the current 16th: after the first tiles almost none do).
 //   k_margin_finish   a_i, b_i, score_i
+#include <stdlib.h>
 #include <string.h>
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -73,6 +74,25 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *tma
             "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// The same load delivered to the same shared-memory offset (and mbarrier offset) of every CTA of the cluster in `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(unsigned dst, const CUtensorMap *tmap, unsigned bar, int c0, int c1, unsigned short mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n" ::
+            "r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO = 64 x 16 B), LBO = 1,
 // descriptor version 1 (Blackwell), layout type 2 (same geometry as dense_tc.cu: 64 fp16 = 32 tf32 = 128 bytes)
 __device__ __forceinline__ uint64_t umma_desc(unsigned smem_addr)
@@ -95,6 +115,12 @@ __device__ __forceinline__ void umma_f16(unsigned tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(unsigned bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` (a stage is free once BOTH CTAs of a pair have read it)
+__device__ __forceinline__ void umma_commit_multicast(unsigned bar, unsigned short mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -158,14 +184,18 @@ __global__ void __launch_bounds__(256) k_margin_pair_dot(const void *x, const vo
 // ---------------------------------------------------------------------------------------------------------------------
 // kNN: avg[i] = mean of the k smallest |q_i - b_j|^2 = qn2[i] - 2 * mean of the k largest (q_i.b_j - bn2[j] / 2)
 // ---------------------------------------------------------------------------------------------------------------------
+// PAIR: the CTAs run as clusters of two that sweep the base in lockstep; each loads ONE half (128 rows) of every base
+// tile and multicasts it into both CTAs' shared memory, so the L2 -> SM traffic per CTA and k-slice drops from 48 KB
+// (16 KB of queries + 32 KB of base) to 32 KB.  The MMAs stay per CTA (cta_group::1, own queries x the whole tile).
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_b, const float *qn2, const float *bn2,
-             int nq, int nb, int dim, int k, float *avg_out)
+k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_bh,
+             const float *qn2, const float *bn2, int nq, int nb, int dim, int k, float *avg_out)
 {
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) unsigned long long bars[2 * kStages + 4];   // full[], empty[], tmem_full[2], tmem_empty[2]
     __shared__ unsigned tmem_slot;
-    __shared__ float hb[2][kBN];                                       // -bn2 / 2 of the tile's columns (-inf past the end)
+    __shared__ __align__(16) float hb[2][kBN];                         // -bn2 / 2 of the tile's columns (-inf past the end)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned char *tiles = reinterpret_cast<unsigned char *>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const unsigned tiles_u32 = smem_u32(tiles);
@@ -175,7 +205,7 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     const int ntiles = (nb + kBN - 1) / kBN, nk = dim / kBK;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -185,8 +215,10 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers exist before either multicasts into the other
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
     const unsigned tmem_d = tmem_slot;
+    const unsigned rank = PAIR ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         // ---- TMA producer ------------------------------------------------------------------------------------
@@ -197,9 +229,13 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                     const int s = it % kStages;
                     mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);          // first lap: passes immediately
                     const unsigned base = tiles_u32 + s * kStageBytes;
-                    mbar_expect_tx(bar_full + 8 * s, kStageBytes);
+                    mbar_expect_tx(bar_full + 8 * s, kStageBytes);                   // own queries + both halves of the base tile
                     tma_load_2d(base, &tm_q, bar_full + 8 * s, ks * kBK, q0);
-                    tma_load_2d(base + kABytes, &tm_b, bar_full + 8 * s, ks * kBK, t * kBN);
+                    if (PAIR)
+                        tma_load_2d_multicast(base + kABytes + rank * (kBBytes / 2), &tm_bh, bar_full + 8 * s, ks * kBK,
+                                              t * kBN + (int)rank * (kBN / 2), (unsigned short)3);
+                    else
+                        tma_load_2d(base + kABytes, &tm_b, bar_full + 8 * s, ks * kBK, t * kBN);
                 }
         }
     } else if (warp == 1) {
@@ -219,7 +255,8 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
 #pragma unroll
                     for (int kk = 0; kk < kBK / 16; ++kk)                            // UMMA K = 16 fp16 = 32 bytes along the row
                         umma_f16(d, umma_desc(a + kk * 32), umma_desc(b + kk * 32), (ks | kk) != 0);
-                    umma_commit(bar_empty + 8 * s);                                  // the stage is free once these MMAs have read it
+                    if (PAIR) umma_commit_multicast(bar_empty + 8 * s, (unsigned short)3);   // ... in both CTAs: the peer writes into this stage too
+                    else umma_commit(bar_empty + 8 * s);                             // the stage is free once these MMAs have read it
                 }
                 umma_commit(bar_tfull + 8 * buf);                                    // the accumulator is complete
             }
@@ -255,14 +292,35 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                // keys of the 32 columns and their maximum: after the first tiles almost no chunk holds a candidate, and the
+                // common path is then 8 LDS.128 + 32 FADD + 32 FMNMX and one branch (an insertion inlined per column made the
+                // epilogue instruction-fetch bound - ncu: stall_no_inst at every reconvergence point - and the MMA warp
+                // waited for its accumulators)
+                float v[32];
+                float vmax = -INFINITY;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float v = __uint_as_float(r[j]) + hb[buf][c0 + j];
-                    if (v > top[kTopK - 1]) {
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 h4 = *reinterpret_cast<const float4 *>(&hb[buf][c0 + j]);
+                    v[j] = __uint_as_float(r[j]) + h4.x; v[j + 1] = __uint_as_float(r[j + 1]) + h4.y;
+                    v[j + 2] = __uint_as_float(r[j + 2]) + h4.z; v[j + 3] = __uint_as_float(r[j + 3]) + h4.w;
+                    vmax = fmaxf(vmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+                }
+                // rare path: take the chunk's maxima one by one while they still beat the current k-th best
+                while (vmax > top[kTopK - 1]) {
+                    int cnt = 0;
 #pragma unroll
-                        for (int i = kTopK - 1; i > 0; --i) top[i] = v > top[i - 1] ? top[i - 1] : (v > top[i] ? v : top[i]);
-                        top[0] = fmaxf(top[0], v);
+                    for (int j = 0; j < 32; ++j) {
+                        cnt += v[j] == vmax;
+                        v[j] = v[j] == vmax ? -INFINITY : v[j];
                     }
+                    for (int c = 0; c < cnt && vmax > top[kTopK - 1]; ++c) {        // equal keys (duplicate vectors) each count
+#pragma unroll
+                        for (int i = kTopK - 1; i > 0; --i) top[i] = vmax > top[i - 1] ? top[i - 1] : (vmax > top[i] ? vmax : top[i]);
+                        top[0] = fmaxf(top[0], vmax);
+                    }
+                    vmax = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) vmax = fmaxf(vmax, v[j]);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -278,6 +336,7 @@ k_margin_knn(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ C
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // the peer may still be multicasting into / arriving on this CTA's shared memory
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "n"(kTmemCols));
 }
@@ -357,16 +416,40 @@ int prepare(const void *rows, int n, int dim, int fp16, __half *out, float *n2, 
 
 int knn(const __half *q, const float *qn2, int nq, const __half *b, const float *bn2, int nb, int dim, int k, float *avg, cudaStream_t st)
 {
-    CUtensorMap tq, tb;
+    CUtensorMap tq, tb, tbh;
     int rc = make_map(&tq, q, nq, dim, kQM);
     if (rc != SVX_OK) return rc;
     if ((rc = make_map(&tb, b, nb, dim, kBN)) != SVX_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SVX_CUDA_OK(cudaFuncSetAttribute(k_margin_knn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set = true;
+    if ((rc = make_map(&tbh, b, nb, dim, kBN / 2)) != SVX_OK) return rc;          // half tiles: what one CTA of a pair loads
+    static const bool pair = !(getenv("SVX_MARGIN_PAIR") && atoi(getenv("SVX_MARGIN_PAIR")) == 0);
+    const int blocks = (nq + kQM - 1) / kQM;
+    if (pair && blocks >= 2) {
+        auto kern = k_margin_knn<true>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((blocks + 1) / 2 * 2));      // whole pairs: the odd CTA out multiplies zero rows
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SVX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tq, tb, tbh, qn2, bn2, nq, nb, dim, k, avg));
+    } else {
+        auto kern = k_margin_knn<false>;
+        static bool attr_set = false;
+        if (!attr_set) {
+            SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+            attr_set = true;
+        }
+        kern<<<blocks, kThreads, kSmemBytes, st>>>(tq, tb, tbh, qn2, bn2, nq, nb, dim, k, avg);
     }
-    k_margin_knn<<<(nq + kQM - 1) / kQM, kThreads, kSmemBytes, st>>>(tq, tb, qn2, bn2, nq, nb, dim, k, avg);
     SVX_LAUNCH_CHECK();
     return SVX_OK;
 }
