@@ -17,11 +17,10 @@
 // and it occupies the FP32 pipe for two cycles per issue: the exact stream needs 1 issue slot per MAC
 // instead of 2, which is what bounded the scalar kernel (issue-active 82 %, FMA pipe 67 %).
 //
-// Tile = ne = 256 / (B/2 + 1) consecutive block-diagonals of one job (2 ne + 1 anti-diagonals, the first and last shared
+// Tile = ne (about 32 CW / (B/2 + 1), see the consumer mapping) consecutive block-diagonals of one job (2 ne + 1 anti-diagonals, the first and last shared
 // with the neighbouring tiles cell by cell - every band cell belongs to exactly one block, so to exactly one tile).
 // B/2 + 1 band slots (Y - Ymin(e)) cover every band cell of a block-diagonal (proved by enumeration in
-// tests/test_host_logic.py); the 256 consumer threads own the (block-diagonal, slot) pairs slot-fastest, so the eight
-// lanes of an LDS.128 phase read consecutive rows (consecutive Y, descending X): no conflicts inside a block-diagonal.
+// tests/test_host_logic.py); the consumer threads own the (block-diagonal, slot) pairs of the tile.
 // Shared-memory layout of one embedding slice (BC floats): x rows as PAIR ROWS, the two positions of a block
 // interleaved float by float ({x[2X][d], x[2X+1][d]} is then one aligned 8-byte word = one FFMA2 operand),
 // staged with 4-byte cp.async; y rows as [even positions | odd positions], 16-byte cp.async; both through a
@@ -95,7 +94,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 // warp covers the FFMA2 dependency stalls the other two leave open, ncu: "wait" + "math throttle" on every other sample)
 template <int K, int BC, int DV, bool EXACT, int CW>
 __global__ void __launch_bounds__(32 * (CW + 4), 1)
-k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, float one, float nz)
+k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, int grouped, float one, float nz)
 {
     constexpr int T = K * (K + 1) / 2;
     constexpr int XS = 2 * BC + 4;      // pair-row stride in floats: 8 consecutive pair rows tile the 32 banks
@@ -223,11 +222,25 @@ k_banded_costs_p2(const SvxBandJob *jobs, int dim, int nstages, int nb, int ne, 
     }
 
     // ---- consumers: this thread's block ----------------------------------------------------------------------
-    // The 32 CW consumer threads take the tile's (block-diagonal, band slot) pairs slot-fastest: thread t owns slot t % nb of
-    // block-diagonal e_first + t / nb, ne = 32 CW / nb block-diagonals per tile.  Every scheduler then runs CW / 4 consumer
-    // warps whatever the band width (a warp per slot gave 9 or 10 warps at bands 16 / 18: 3 + 2 + 2 + 2 per scheduler),
-    // and the eight lanes of an LDS.128 phase read consecutive rows (consecutive slots = consecutive Y, descending X).
-    const int ei = tid / nb, yi = tid - ei * nb;
+    // Consumer thread -> (block-diagonal of the tile, band slot).  Both orders give every scheduler CW / 4 consumer warps
+    // whatever the band width (a warp per slot gave 9 or 10 warps at bands 16 / 18: 3 + 2 + 2 + 2 per scheduler).
+    //   grouped: 4 CW groups of eight lanes, group g owns slot g % nb of the eight consecutive block-diagonals
+    //     8 (g / nb) ..: ne = 8 * (4 CW / nb).  The eight lanes of an LDS.128 phase - one group - read rows that are equal
+    //     or consecutive (X and Y advance by 0 or 1 along e): no bank conflicts, but 4 CW mod nb groups idle.
+    //   slot-fastest: thread t owns slot t % nb of block-diagonal t / nb: ne = 32 CW / nb, at most nb - 1 idle lanes, and
+    //     two-way conflicts in the phases that straddle a block-diagonal when nb is not a multiple of 8.
+    // The launcher takes the grouped order unless it idles more than 7 % of the lanes the other would use (measured:
+    // band 18, nb = 10: grouped 2 % faster with 24 against 25 block-diagonals; band 16, nb = 9: slot-fastest 10 % faster
+    // with 28 against 24; the two coincide at nb = 8).
+    int ei, yi;
+    if (grouped) {
+        const int grp = tid >> 3, eb = grp / nb;
+        yi = grp - eb * nb;
+        ei = 8 * eb + (tid & 7);
+    } else {
+        ei = tid / nb;
+        yi = tid - ei * nb;
+    }
     const int e = e_first + ei;
     const bool in_tile = ei < ne;
     const int dA = 2 * e, dB = 2 * e + 1, dC = 2 * e + 2;
@@ -342,8 +355,11 @@ int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int di
     constexpr int kConsWarps = CW;
     const int nb = band / 2 + 1;                                   // band slots (2 x 2 blocks) per block-diagonal
     if (nb > 32 * kConsWarps) return -1;
-    int ne = 32 * kConsWarps / nb;                                 // block-diagonals per tile
+    const int ne_grouped = 8 * (4 * kConsWarps / nb);              // block-diagonals per tile, see the consumer mapping
+    int ne = 32 * kConsWarps / nb;
     if (ne > 5 * CW) ne = 5 * CW;
+    const int grouped = ne_grouped * 100 >= ne * 93;
+    if (grouped) ne = ne_grouped;
     if (nprod < 1) nprod = 1;
     if (nprod > 4) nprod = 4;
     const int threads = 32 * (kConsWarps + nprod);
@@ -358,11 +374,11 @@ int launch_p2_t(const SvxBandJob *jobs_d, int nj, int max_alen, int band, int di
     if (mode == SVX_COST_EXACT) {
         auto kern = k_banded_costs_p2<K, BC, DV, true, CW>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, grouped, 1.0f, -0.0f);
     } else {
         auto kern = k_banded_costs_p2<K, BC, DV, false, CW>;
         SVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, 1.0f, -0.0f);
+        kern<<<grid, threads, smem, st>>>(jobs_d, dim, nstages, nb, ne, grouped, 1.0f, -0.0f);
     }
     SVX_LAUNCH_CHECK();
     return SVX_OK;
