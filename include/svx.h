@@ -192,9 +192,11 @@ typedef struct SvxDenseJob {
     const float *n1;           /* (s1)                                                   */
     float *costs;              /* (s0, s1) output of svx_dense_costs                     */
     float *dots;               /* (s0, s1) or NULL: the raw dot products v0[x].v1[y]     */
-    const void *tmap0;         /* device copies (64-byte aligned, 128 B each) of the TMA */
-    const void *tmap1;         /*   descriptors of v0 / v1 (svx_dense_tmaps_encode); only */
-                               /*   read when mode == SVX_COST_TC                         */
+    const void *tmap0;         /* SVX_COST_TC only: device copies (64-byte aligned) of   */
+    const void *tmap1;         /*   the TMA descriptor PAIRS {v0, lo0} / {v1, lo1}, 256 B */
+                               /*   each (svx_dense_tmaps_encode)                         */
+    float *lo0;                /* SVX_COST_TC only: (s0, dim) / (s1, dim) scratch for the */
+    float *lo1;                /*   3xTF32 residual planes, written by svx_dense_costs    */
     const double *del_penalty; /* (1); narrowed to fp32 as dense_dp(float pen) does      */
     uint8_t *bp;               /* (s0+1, s1+1) backpointers 0/1/2, 4 at the origin       */
     double *csum;              /* (s0+1, s1+1) or NULL (debug/parity only)               */
@@ -209,9 +211,10 @@ typedef struct SvxDenseJob {
 SVX_API int svx_dense_costs(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, int dim, int mode,
                     void *stream);
 SVX_API int svx_dense_dp(const SvxDenseJob *jobs_d, const SvxDenseJob *jobs_h, int njobs, void *stream);
-/* Host only: encodes the two CUtensorMap descriptors (128 B each; rows x dim fp32, 128-row x 32-float
- * boxes, 128-byte swizzle) of every job's v0 / v1 into out_host[2*j], out_host[2*j+1].  The caller
- * copies them to the device and sets tmap0 / tmap1 before calling svx_dense_costs(SVX_COST_TC). */
+/* Host only: encodes the four CUtensorMap descriptors (128 B each; rows x dim fp32, 128-row x 32-float
+ * boxes, 128-byte swizzle) of every job's v0, lo0, v1, lo1 into out_host[4*j .. 4*j+3] (lo0 / lo1 must be
+ * set).  The caller copies them to the device and points tmap0 at the first pair and tmap1 at the second
+ * before calling svx_dense_costs(SVX_COST_TC), which first fills lo0 / lo1 (the 3xTF32 residual planes). */
 SVX_API int svx_dense_tmaps_encode(const SvxDenseJob *jobs_h, int njobs, int dim, void *out_host);
 
 /* Length of the search path built from a coarse alignment of (c0,c1) segments for a target level
@@ -331,7 +334,7 @@ enum {
     SVX_PO_IDX0, SVX_PO_IDX1, SVX_PO_XI, SVX_PO_YI, SVX_PO_DELPEN, SVX_PO_TMAPS,
     SVX_PO_NORMS0, SVX_PO_NORMS1, SVX_PO_VEC0, SVX_PO_VEC1, SVX_PO_MEAN0, SVX_PO_MEAN1, SVX_PO_MBAR0, SVX_PO_MBAR1,
     SVX_PO_SCORES, SVX_PO_PERM, SVX_PO_DCOST, SVX_PO_DDOTS, SVX_PO_DBP, SVX_PO_DCSUM, SVX_PO_YPATH, SVX_PO_BCOST,
-    SVX_PO_BBP, SVX_PO_BCSUM, SVX_PO_RECS, SVX_PO_NRECS, SVX_PO_STATUS, SVX_PO_COUNT
+    SVX_PO_BBP, SVX_PO_BCSUM, SVX_PO_RECS, SVX_PO_NRECS, SVX_PO_STATUS, SVX_PO_DLO0, SVX_PO_DLO1, SVX_PO_COUNT
 };
 /* int64 arrays of a plan: per pair (FIRST, NLEV, DEPTH, TOP_REC, TGT_REC), per record, per RNG call */
 enum {

@@ -37,7 +37,7 @@ GATHER = np.dtype([("rows", _P), ("table", _P), ("out", _P), ("nan_rows", _P),
 SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
                   ("scores", _P), ("del_penalty", _P), ("perm", _P), ("dots", _P),
                   ("ne", np.int32), ("nf", np.int32), ("nsamp", np.int32)], align=True)
-DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("dots", _P), ("tmap0", _P), ("tmap1", _P), ("del_penalty", _P),
+DENSE = np.dtype([("v0", _P), ("v1", _P), ("n0", _P), ("n1", _P), ("costs", _P), ("dots", _P), ("tmap0", _P), ("tmap1", _P), ("lo0", _P), ("lo1", _P), ("del_penalty", _P),
                   ("bp", _P), ("csum", _P), ("ypath", _P), ("status_d", _P),
                   ("s0", np.int32), ("s1", np.int32), ("t0", np.int32), ("t1", np.int32),
                   ("upsample", np.int32), ("path_len", np.int32)], align=True)

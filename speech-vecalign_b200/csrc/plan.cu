@@ -196,7 +196,7 @@ extern "C" int svx_plan_create(const SvxAlignParams *prm, int npairs, const int3
     lay(SVX_PO_XI, [&](int64_t r) { return pl->has_draw[r] ? pl->nsamp[r] * 4 : 0; });
     lay(SVX_PO_YI, [&](int64_t r) { return pl->has_draw[r] ? pl->nsamp[r] * 4 : 0; });
     lay(SVX_PO_DELPEN, [&](int64_t) { return (int64_t)8; });
-    lay(SVX_PO_TMAPS, [&](int64_t r) { return (pl->is_top[r] && tc) ? (int64_t)256 : 0; });
+    lay(SVX_PO_TMAPS, [&](int64_t r) { return (pl->is_top[r] && tc) ? (int64_t)512 : 0; });
     {
         const int64_t nstage = std::max(1, pl->lmax);
         pl->jobs_cap = 2 * P * (int64_t)sizeof(SvxRows) + 2 * R * (int64_t)sizeof(SvxDownJob) + 2 * R * (int64_t)sizeof(SvxNormJob) +
@@ -227,6 +227,8 @@ extern "C" int svx_plan_create(const SvxAlignParams *prm, int npairs, const int3
     lay(SVX_PO_BCOST, [&](int64_t r) { return pl->A[r] * pl->T[r] * band * 4; });
     lay(SVX_PO_BBP, [&](int64_t r) { return pl->banded[r] ? (pl->A[r] + 2) * band : 0; });
     lay(SVX_PO_BCSUM, [&](int64_t r) { return pl->banded[r] ? (pl->A[r] + 2) * band * 8 : 0; });
+    lay(SVX_PO_DLO0, [&](int64_t r) { return (pl->is_top[r] && tc) ? rs0[r] * D * 4 : 0; });   // 3xTF32 residual planes
+    lay(SVX_PO_DLO1, [&](int64_t r) { return (pl->is_top[r] && tc) ? rs1[r] * D * 4 : 0; });
     // alignment records: the level-0 ones (the results) first and contiguous, so that reading the results back moves
     // only them; the coarser levels' records (consumed on the device by the next level's path builder) follow
     pl->off[SVX_PO_RECS].assign(R, 0);
@@ -445,7 +447,9 @@ extern "C" int svx_plan_bind(SvxPlan *pl, void *arena_d, void *stage_h, const vo
         j->upsample = pl->depth[p] > 0; j->path_len = (int32_t)pl->A[g];
         if (prm.cost_mode == SVX_COST_TC) {
             j->tmap0 = at(SVX_PO_TMAPS, t);
-            j->tmap1 = at(SVX_PO_TMAPS, t) + 128;
+            j->tmap1 = at(SVX_PO_TMAPS, t) + 256;
+            j->lo0 = (float *)at(SVX_PO_DLO0, t);
+            j->lo1 = (float *)at(SVX_PO_DLO1, t);
         }
     }
     const int as = new_arr();
@@ -518,11 +522,11 @@ extern "C" int svx_plan_bind(SvxPlan *pl, void *arena_d, void *stage_h, const vo
     // ---- staging block: default penalties, TMA descriptors, descriptor arrays ----------------------------------------
     for (int64_t r = 0; r < R; ++r) memcpy(pl->stage + pl->off[SVX_PO_DELPEN][r], &pl->fallback_pen, 8);
     if (prm.cost_mode == SVX_COST_TC && P) {
-        std::vector<uint8_t> blobs((size_t)P * 256);
+        std::vector<uint8_t> blobs((size_t)P * 512);
         const JobArr &da = pl->arrays[ad];
         const int rc = svx_dense_tmaps_encode(reinterpret_cast<const SvxDenseJob *>(da.host.data()), P, prm.dim, blobs.data());
         if (rc != SVX_OK) return rc;
-        for (int p = 0; p < P; ++p) memcpy(pl->stage + pl->off[SVX_PO_TMAPS][pl->top_rec[p]], blobs.data() + (size_t)p * 256, 256);
+        for (int p = 0; p < P; ++p) memcpy(pl->stage + pl->off[SVX_PO_TMAPS][pl->top_rec[p]], blobs.data() + (size_t)p * 512, 512);
     }
     int64_t cur = pl->jobs_off;
     for (auto &a : pl->arrays) {

@@ -156,11 +156,13 @@ def make_dense_costs(vecs0, vecs1, norm0, norm1, offset0=0, offset1=0, cost_mode
     job = np.zeros(1, dtype=capi.DENSE)
     job["v0"], job["v1"], job["n0"], job["n1"], job["costs"] = _ptr(ta), _ptr(tb), _ptr(tna), _ptr(tnb), costs.data_ptr()
     job["s0"], job["s1"] = s0, s1
-    if cost_mode == capi.SVX_COST_TC:      # tcgen05 path: TMA descriptors encoded on the host
-        blobs = np.zeros((1, 2, 128), dtype=np.uint8)
+    if cost_mode == capi.SVX_COST_TC:      # tcgen05 path: residual-plane scratch; TMA descriptors encoded on the host
+        lo0, lo1 = _empty(max(1, s0 * d), torch.float32), _empty(max(1, s1 * d), torch.float32)
+        job["lo0"], job["lo1"] = lo0.data_ptr(), lo1.data_ptr()
+        blobs = np.zeros((1, 4, 128), dtype=np.uint8)
         capi.check(capi.lib().svx_dense_tmaps_encode(capi.hptr(job), 1, d, capi.hptr(blobs)), "svx_dense_tmaps_encode")
         tm = _up(blobs.reshape(-1))
-        job["tmap0"], job["tmap1"] = tm.data_ptr(), tm.data_ptr() + 128
+        job["tmap0"], job["tmap1"] = tm.data_ptr(), tm.data_ptr() + 256
     _launch(capi.lib().svx_dense_costs, "svx_dense_costs", job, d, cost_mode)
     return costs[:s0 * s1].cpu().numpy().reshape(s0, s1)
 

@@ -33,7 +33,7 @@ def host_threads(cap=16):
 
 _OFF_KEYS = ["idx0", "idx1", "xi", "yi", "delpen", "tmaps", "norms0", "norms1", "vec0", "vec1", "mean0", "mean1", "mbar0",
              "mbar1", "scores", "perm", "dcost", "ddots", "dbp", "dcsum", "ypath", "bcost", "bbp", "bcsum", "recs", "nrecs",
-             "status"]                       # include/svx.h SVX_PO_*
+             "status", "dlo0", "dlo1"]       # include/svx.h SVX_PO_*
 _PA = {name: i for i, name in enumerate(
     ["first", "nlev", "depth", "rec_pair", "rec_level", "rs0", "rs1", "A", "T", "banded", "rec_cap", "nsamp", "has_draw",
      "top_rec", "tgt_rec", "draw_pair", "draw_high", "draw_count", "draw_off", "draw_begin"])}      # SVX_PA_*
