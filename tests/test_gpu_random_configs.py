@@ -203,7 +203,9 @@ def test_random_configurations_other_cost_modes(svb, oracle, mode, bar):
     near-ties."""
     from speech_vecalign_b200 import synth
     differ = 0
-    cases = _draw_cases(30, 555)
+    ncases = int(os.environ.get("SVX_FUZZ_MODE_CASES", "30"))       # soak: SVX_FUZZ_MODE_CASES=700
+    cases = _draw_cases(ncases, 555)
+    worst = 0.0
     for case in cases:
         a, k = case["a"], case["a"] - 1
         v0, v1 = synth.synth_pair(case["n0"], case["n1"], k, dim=case["dim"], seed=case["seed"])
@@ -215,8 +217,13 @@ def test_random_configurations_other_cost_modes(svb, oracle, mode, bar):
         top = max(ref)
         err = np.max(np.abs(got[top]["costs_1to1"].astype(np.float64) - ref[top]["costs_1to1"]), initial=0)
         assert err <= bar, (case, err)
+        worst = max(worst, float(err))
         differ += not same_alignments(got[0]["final_alignments"], ref[0]["final_alignments"])
-    assert differ <= 2, differ
+    log = os.environ.get("SVX_FUZZ_MODE_LOG")
+    if log:
+        with open(log, "a") as f:
+            f.write(json.dumps({"mode": mode, "cases": ncases, "final_alignment_differs": differ, "max_top_cost_err": worst}) + "\n")
+    assert differ <= max(2, ncases // 15), differ
 
 
 def _draw_skewed(n, seed):
