@@ -70,6 +70,8 @@ def parse_args():
                     help="pair groups on separate CUDA streams (1 = one serial chain; 0 = auto: 4 below 128 pairs, else 1 - "
                          "large batches already amortise the latency-bound wavefront kernels)")
     ap.add_argument("--unfused-prologue", action="store_true", help="A/B: the three separate prologue launchers")
+    ap.add_argument("--widen-pass", action="store_true",
+                    help="A/B (cfg4): widen the resident fp16 rows to fp32 in a separate pass instead of reading them from the prologue")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="default workload without the all_configs block")
@@ -563,7 +565,7 @@ def bench_cfg4(ctx, corpus_pairs, steps, warmup, e2e_steps, with_cpu, with_clock
     torch = ctx.torch
     import speech_vecalign_b200 as svb
     from speech_vecalign_b200 import capi, synth
-    from speech_vecalign_b200.engine import BatchRun, WidenJobs, make_params, workspace_bytes
+    from speech_vecalign_b200.engine import BatchRun, WidenJobs, make_params, row_sources, workspace_bytes
     from speech_vecalign_b200.sharding import estimate_work, gather_in_order, lpt_partition
     args, rank, world, dev = ctx.args, ctx.rank, ctx.world, ctx.dev
     lib = capi.lib()
@@ -611,11 +613,15 @@ def bench_cfg4(ctx, corpus_pairs, steps, warmup, e2e_steps, with_cpu, with_clock
     for c in range(len(bounds) - 1):
         lo, hi = bounds[c], bounds[c + 1]
         wv = views(work, lo, hi, base=int(off0[lo]))
-        widen = WidenJobs([t for pr in sv[lo:hi] for t in pr], [t for pr in wv for t in pr], DIM, dev)
+        # the resident fp16 rows are the SOURCES of the level-0 prologue (read once, 2 bytes per element; the normalised
+        # fp32 rows land in the shared work buffer); --widen-pass restores the separate widening pass (fp16 -> fp32
+        # tensor -> prologue) that the unfused prologue still needs
+        widen = WidenJobs([t for pr in sv[lo:hi] for t in pr], [t for pr in wv for t in pr], DIM, dev) if args.widen_pass else None
+        srcs = None if args.widen_pass else (row_sources([t0 for t0, _ in sv[lo:hi]]), row_sources([t1 for _, t1 in sv[lo:hi]]))
         run = BatchRun([t0.data_ptr() for t0, _ in wv], [t1.data_ptr() for _, t1 in wv], n0[lo:hi], n1[lo:hi], k, k, DIM, types,
                        PARAMS["del_percentile_frac"], w, PARAMS["max_size_full_dp"], PARAMS["costs_sample_size"],
                        PARAMS["num_samps_for_norm"], dev, cost_mode=mode, seeds=[int(g) for g in mine[lo:hi]], arena=arena,
-                       fused_prologue=not args.unfused_prologue)
+                       fused_prologue=not args.unfused_prologue, sources=srcs)
         run.keep_init_on_device()                 # the chunks take turns in one arena: descriptors + draws are restored device to device
         chunks.append((lo, hi, widen, run))
     cells = sum(ch[3].dp_cells() for ch in chunks)
@@ -627,14 +633,16 @@ def bench_cfg4(ctx, corpus_pairs, steps, warmup, e2e_steps, with_cpu, with_clock
             if timing is not None:
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record()
-            widen.run()                           # fp16 -> fp32 working tensors (the path normalises them in place)
+            if widen is not None:
+                widen.run()                       # fp16 -> fp32 working tensors (the path normalises them in place)
             if timing is not None:
                 b_.record()
             run.upload()                          # descriptors + draws of this chunk (the arena is shared)
             run.run(timing=timing is not None, ngroups=1)
             if timing is not None:
                 kt = run.kernel_times()
-                kt["svx_widen_fp16"] = a_.elapsed_time(b_)
+                if widen is not None:
+                    kt["svx_widen_fp16"] = a_.elapsed_time(b_)
                 for nm, ms in kt.items():
                     timing[nm] = timing.get(nm, 0.0) + ms
             if collect is not None:
@@ -721,7 +729,8 @@ def bench_cfg4(ctx, corpus_pairs, steps, warmup, e2e_steps, with_cpu, with_clock
             alg[nm] = alg.get(nm, 0) + v
         for nm, v in run.cost_flops().items():
             flops[nm] = flops.get(nm, 0) + v
-    alg["svx_widen_fp16"] = int(off0[-1]) * 6
+    if args.widen_pass:
+        alg["svx_widen_fp16"] = int(off0[-1]) * 6
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     kernels, roofline, serial_ms = launcher_report(ctx, ktimes, alg, flops, "cfg4", args.cost_mode, sm_mhz)
 
@@ -752,7 +761,8 @@ def bench_cfg4(ctx, corpus_pairs, steps, warmup, e2e_steps, with_cpu, with_clock
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "corpus_pairs": corpus_pairs, "pairs_on_rank0": P, "chunk_pairs": CFG4_CHUNK, "alignment_max_size": a,
                    "dim": DIM, "cost_mode": args.cost_mode, "partition": "sharding.lpt_partition on sharding.estimate_work",
-                   "resident_dtype": "fp16 (.embed on-disk dtype), widened to fp32 on the device inside the step",
+                   "resident_dtype": "fp16 (.embed on-disk dtype), " + ("widened to fp32 by a separate pass inside the step" if args.widen_pass else
+                                                                      "read by the level-0 prologue inside the step (row sources)"),
                    "l2": f"rank 0 streams {int(off0[-1]) * 2 / 2**30:.2f} GiB of fp16 embeddings per step > 126 MB L2", **PARAMS},
         "dp_cells_per_sec": cells_all * steps / (total_ms * 1e-3),
         "alignments_per_step": n_align, "pairs_with_device_error": bad, "gather_to_rank0_s": t_g,

@@ -134,6 +134,17 @@ SVX_API int svx_gather_doc_embedding(const SvxGatherJob *jobs_d, const SvxGather
  * the number of passes changes.  Both sides of a pair must be in the same call (step 2 of every job
  * runs before step 3 of any job).
  * ---------------------------------------------------------------------------------------------- */
+/* Optional source of a level's raw rows: the (k, n, dim) tensor that svx_gather_doc_embedding would have written -
+ * rows[table[o, i]] widened to fp32, a zero row for table < 0, a row index outside [0, nrows) or a source row holding a
+ * NaN (embedding_utils.py:135-203) - is read THROUGH the table by the prologue's level-0 pass instead of being written
+ * to HBM first and read back (for fp16 .embed rows: 2 bytes read per element instead of 2 read + 4 written + 4 read). */
+typedef struct SvxRowSource {
+    const void *rows;        /* (nrows, dim) fp16 or fp32; NULL = no source: the raw rows are in SvxLevelJob.vecs */
+    const int32_t *table;    /* (k, n) source row of every (overlap, position), -1 = zeros; NULL = identity       */
+    int32_t *nan_rows;       /* (1) or NULL: += number of (overlap, position) rows zeroed because of NaNs          */
+    int32_t nrows, is_fp16;
+} SvxRowSource;
+
 typedef struct SvxLevelJob {
     float *vecs;             /* (k, n, dim) raw rows (level 0) or un-centred pair sums; finished in place */
     float *mean;             /* (k, dim) scratch for the mean rows, NULL at level 0 (nothing to subtract) */
@@ -147,6 +158,9 @@ typedef struct SvxLevelJob {
     int32_t keep;            /* overlaps [0, keep) get their finished rows and norms stored; the others
                                 are only normalised on the fly for the pair sums (levels >= 1 align
                                 1-1 only: overlap 0 is all the later kernels read).  keep = k stores all. */
+    SvxRowSource src;        /* src.rows != NULL (mean must be NULL): the raw rows come from here and the */
+    SvxRowSource osrc;       /*   finished rows go to `vecs`; osrc likewise replaces `other` (its         */
+                             /*   nan_rows is not used: the other side's own job counts them)             */
 } SvxLevelJob;
 SVX_API int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *jobs_h, int njobs, int dim, void *stream);
 
@@ -348,6 +362,10 @@ SVX_API int svx_plan_create(const SvxAlignParams *params, int npairs, const int3
 SVX_API void svx_plan_destroy(SvxPlan *plan);
 SVX_API int svx_plan_info(const SvxPlan *plan, SvxPlanInfo *info);
 SVX_API int svx_plan_array(const SvxPlan *plan, int which, const int64_t **ptr, int64_t *count);   /* borrowed */
+/* Optional, before svx_plan_bind: per-pair sources of the level-0 rows (arrays of npairs entries, copied; NULL, NULL
+ * clears them).  v0_d[p] / v1_d[p] of svx_plan_bind are then pure outputs (the normalised fp32 rows).  Needs the fused
+ * prologue (SvxPlanInfo.fused_prologue); SVX_ERR_UNSUPPORTED otherwise - gather with svx_gather_doc_embedding then. */
+SVX_API int svx_plan_set_sources(SvxPlan *plan, const SvxRowSource *src0, const SvxRowSource *src1);
 /* Writes default penalties, TMA descriptors and every job descriptor for (arena_d, v0_d[p], v1_d[p]) into stage_h. */
 SVX_API int svx_plan_bind(SvxPlan *plan, void *arena_d, void *stage_h, const void *const *v0_d, const void *const *v1_d);
 /* The reference's np.random draws (np.random.choice(range(n), size=k), dp_utils.py:301-302,346) written into the

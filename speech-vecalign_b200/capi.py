@@ -28,10 +28,11 @@ DOWN = np.dtype([("in", _P), ("out", _P), ("mean", _P), ("k", np.int32), ("n", n
 NORM = np.dtype([("vecs", _P), ("other", _P), ("idx", _P), ("mbar", _P), ("norms", _P),
                  ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32)],
                 align=True)
+ROW_SOURCE = np.dtype([("rows", _P), ("table", _P), ("nan_rows", _P), ("nrows", np.int32), ("is_fp16", np.int32)], align=True)
 LEVEL = np.dtype([("vecs", _P), ("mean", _P), ("next", _P), ("other", _P), ("other_mean", _P), ("idx", _P),
                   ("mbar", _P), ("norms", _P),
                   ("k", np.int32), ("n", np.int32), ("ko", np.int32), ("no", np.int32), ("per", np.int32),
-                  ("keep", np.int32)], align=True)
+                  ("keep", np.int32), ("src", ROW_SOURCE), ("osrc", ROW_SOURCE)], align=True)
 GATHER = np.dtype([("rows", _P), ("table", _P), ("out", _P), ("nan_rows", _P),
                    ("k", np.int32), ("n", np.int32), ("nrows", np.int32), ("is_fp16", np.int32)], align=True)
 SCORE = np.dtype([("e", _P), ("f", _P), ("norm_e", _P), ("norm_f", _P), ("xi", _P), ("yi", _P),
@@ -64,7 +65,7 @@ PLAN_INFO = np.dtype([("npairs", np.int32), ("nrecords", np.int32), ("max_depth"
                       ("result_offset", np.int64), ("result_bytes", np.int64), ("counts_offset", np.int64),
                       ("fallback_del_penalty", np.float64)], align=True)
 
-_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER, PARAMS, PLAN_INFO]
+_STRUCTS = [ROWS, DOWN, NORM, SCORE, DENSE, BAND, REC, LEVEL, GATHER, PARAMS, PLAN_INFO, ROW_SOURCE]
 
 _lib = None
 
@@ -121,6 +122,7 @@ def lib():
         "svx_plan_info": [vp, vp],
         "svx_plan_array": [vp, ci, vp, vp],
         "svx_plan_bind": [vp, vp, vp, vp, vp],
+        "svx_plan_set_sources": [vp, vp, vp],
         "svx_plan_draw_seeded": [vp, vp, ci],
         "svx_plan_draw_stream": [vp, vp, vp],
         "svx_plan_upload": [vp, ci, vp],
@@ -158,7 +160,7 @@ EXPORTED_SYMBOLS = [
     "svx_banded_dp", "svx_host_banded_dp", "svx_host_dense_dp", "svx_host_randint_stream",
     "svx_host_randint_seeded", "svx_upload_pinned", "svx_host_memcpy", "svx_version",
     "svx_last_error_string", "svx_sizeof_job", "svx_launch_count",
-    "svx_plan_create", "svx_plan_destroy", "svx_plan_info", "svx_plan_array", "svx_plan_bind", "svx_plan_draw_seeded",
+    "svx_plan_create", "svx_plan_destroy", "svx_plan_info", "svx_plan_array", "svx_plan_bind", "svx_plan_set_sources", "svx_plan_draw_seeded",
     "svx_plan_draw_stream", "svx_plan_upload", "svx_plan_restore", "svx_plan_launcher_name", "svx_plan_enqueue", "svx_plan_fetch",
     "svx_workspace_bytes", "svx_align_batch", "svx_margin_workspace_bytes", "svx_margin_scores",
     "svx_host_overlap_tables",

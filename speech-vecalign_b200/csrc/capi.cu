@@ -40,6 +40,7 @@ extern "C" int svx_sizeof_job(int which)
         case 8: return (int)sizeof(SvxGatherJob);
         case 9: return (int)sizeof(SvxAlignParams);
         case 10: return (int)sizeof(SvxPlanInfo);
+        case 11: return (int)sizeof(SvxRowSource);
         default: return -1;
     }
 }

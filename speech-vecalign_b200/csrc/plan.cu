@@ -59,6 +59,7 @@ struct SvxPlan {
     unsigned char *stage = nullptr;
     bool bound = false;
     double fallback_pen = 0.0;
+    std::vector<SvxRowSource> src0, src1;          // optional sources of the level-0 rows (svx_plan_set_sources)
 };
 
 namespace {
@@ -328,6 +329,25 @@ extern "C" int svx_plan_array(const SvxPlan *pl, int which, const int64_t **ptr,
 // ------------------------------------------------------------------------------------------------------------------
 // Binding: descriptors for a concrete arena and concrete input tensors.
 // ------------------------------------------------------------------------------------------------------------------
+extern "C" int svx_plan_set_sources(SvxPlan *pl, const SvxRowSource *src0, const SvxRowSource *src1)
+{
+    SVX_REQUIRE(pl, SVX_ERR_ARG, "svx_plan_set_sources: null plan");
+    SVX_REQUIRE((src0 == nullptr) == (src1 == nullptr), SVX_ERR_ARG, "svx_plan_set_sources: give the sources of both sides or of none");
+    pl->src0.clear();
+    pl->src1.clear();
+    pl->bound = false;
+    if (!src0) return SVX_OK;
+    SVX_REQUIRE(pl->fused, SVX_ERR_UNSUPPORTED,
+                "svx_plan_set_sources: this plan runs the unfused prologue (more than %d norm samples per side, or requested); "
+                "materialise the rows with svx_gather_doc_embedding instead", kMaxFusedSamples);
+    for (int p = 0; p < pl->P; ++p)
+        SVX_REQUIRE(src0[p].rows && src1[p].rows && src0[p].nrows >= 0 && src1[p].nrows >= 0, SVX_ERR_ARG,
+                    "svx_plan_set_sources: pair %d has no source rows", p);
+    pl->src0.assign(src0, src0 + pl->P);
+    pl->src1.assign(src1, src1 + pl->P);
+    return SVX_OK;
+}
+
 extern "C" int svx_plan_bind(SvxPlan *pl, void *arena_d, void *stage_h, const void *const *v0_d, const void *const *v1_d)
 {
     SVX_REQUIRE(pl && (pl->P == 0 || (arena_d && stage_h && v0_d && v1_d)), SVX_ERR_ARG, "svx_plan_bind: null argument");
@@ -383,6 +403,11 @@ extern "C" int svx_plan_bind(SvxPlan *pl, void *arena_d, void *stage_h, const vo
                     j->per = side ? per0 : per1;
                     // levels >= 1 align 1-1 only: later kernels read overlap 0 (debug keeps everything)
                     j->keep = (lvl == 0 || keep) ? j->k : std::min(1, j->k);
+                    if (lvl == 0 && !pl->src0.empty()) {
+                        j->src = side ? pl->src1[p] : pl->src0[p];
+                        j->osrc = side ? pl->src0[p] : pl->src1[p];
+                        j->osrc.nan_rows = nullptr;
+                    }
                 }
             }
             add(L_LEVEL, ai, "svx_level_prologue");

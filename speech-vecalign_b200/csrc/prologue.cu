@@ -76,6 +76,45 @@ __device__ __forceinline__ void warp_unit_row(float4 (&v)[DIM / 128], float *sq,
     }
 }
 
+// Row r = o * n + i of a level whose raw rows come from a source (SvxRowSource): the lane's elements
+// b * 128 + 4 * lane .. + 3 of every 128-float block, exactly what svx_gather_doc_embedding would have written
+// (widened fp16 / fp32, zeros without a source row, zeros when the source row holds a NaN).  Warp-uniform return
+// value: the row was zeroed because of a NaN.
+template <int DIM>
+__device__ __forceinline__ bool warp_source_row(const SvxRowSource &src, int64_t r, int lane, float4 (&v)[DIM / 128])
+{
+    constexpr int NB = DIM / 128;
+    const int s = src.table ? __ldg(src.table + r) : (int)r;
+    const bool have = s >= 0 && s < src.nrows;
+    bool bad = false;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have) {
+        if (src.is_fp16) {
+            const __half *p = reinterpret_cast<const __half *>(src.rows) + (size_t)s * DIM + 4 * lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p + b * 128));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+                v[b] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+        } else {
+            const float *p = reinterpret_cast<const float *>(src.rows) + (size_t)s * DIM + 4 * lane;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) v[b] = ldg_f4(p + b * 128);
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) bad |= (v[b].x != v[b].x) | (v[b].y != v[b].y) | (v[b].z != v[b].z) | (v[b].w != v[b].w);
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (bad) {
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    return bad;
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) k_normalize(const SvxRows *jobs)
 {
@@ -429,9 +468,11 @@ __global__ void __launch_bounds__(256) k_level_sample_den(const SvxLevelJob *job
     const int o = s / job.per;
     const float *p = job.other + ((size_t)o * job.no + job.idx[s]) * DIM;
     float4 v[NB];
+    // a sampled row that the source zeroes because of a NaN is flagged to step (b) by a negative denominator
+    const bool zeroed = job.osrc.rows ? warp_source_row<DIM>(job.osrc, (int64_t)o * job.no + job.idx[s], lane, v) : false;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        v[b] = ldg_f4(p + b * 128 + 4 * lane);
+        if (!job.osrc.rows) v[b] = ldg_f4(p + b * 128 + 4 * lane);
         if (job.other_mean) {
             const float4 g = ldg_f4(job.other_mean + (size_t)o * DIM + b * 128 + 4 * lane);
             v[b].x = __fsub_rn(v[b].x, g.x); v[b].y = __fsub_rn(v[b].y, g.y);
@@ -444,7 +485,10 @@ __global__ void __launch_bounds__(256) k_level_sample_den(const SvxLevelJob *job
     }
     __syncwarp();
     const float total = np_pairwise_from_smem<DIM>(scratch[warp], lane);
-    if (lane == 0) den[s] = __fadd_rn(__fsqrt_rn(total), 1e-5f);
+    if (lane == 0) {
+        const float d = __fadd_rn(__fsqrt_rn(total), 1e-5f);
+        den[s] = zeroed ? -d : d;
+    }
 }
 
 __global__ void __launch_bounds__(128) k_level_sample_acc(const SvxLevelJob *jobs, int dim)
@@ -455,26 +499,37 @@ __global__ void __launch_bounds__(128) k_level_sample_acc(const SvxLevelJob *job
     const int c = blockIdx.x * 128 + threadIdx.x;
     const float *den = reinterpret_cast<const float *>(job.mbar + dim);
     double acc = 0.0;
+    const SvxRowSource &os = job.osrc;
     for (int o = 0; o < job.ko; ++o) {
         const float *base = job.other + (size_t)o * job.no * dim + c;
         const float mu = job.other_mean ? __ldg(job.other_mean + (size_t)o * dim + c) : 0.0f;
         const int32_t *ix = job.idx + (size_t)o * job.per;
         const float *dn = den + (size_t)o * job.per;
+        // element c of sampled row `row` of overlap o, raw: from `other`, or through the source (zeros without a
+        // source row and - flagged by step (a) with a negative denominator - for a source row holding a NaN)
+        auto element = [&](int row, float d) -> float {
+            if (!os.rows) return __ldg(base + (size_t)row * dim);
+            const int64_t r = (int64_t)o * job.no + row;
+            const int sr = os.table ? __ldg(os.table + r) : (int)r;
+            if (d < 0.0f || sr < 0 || sr >= os.nrows) return 0.0f;
+            return os.is_fp16 ? __half2float(__ldg(reinterpret_cast<const __half *>(os.rows) + (size_t)sr * dim + c))
+                              : __ldg(reinterpret_cast<const float *>(os.rows) + (size_t)sr * dim + c);
+        };
         int s = 0;
         for (; s + 4 <= job.per; s += 4) {
             float x[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = __ldg(base + (size_t)__ldg(ix + s + u) * dim);
+            for (int u = 0; u < 4; ++u) x[u] = element(__ldg(ix + s + u), dn[s + u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const float xc = job.other_mean ? __fsub_rn(x[u], mu) : x[u];
-                acc += (double)__fdiv_rn(xc, dn[s + u]);
+                acc += (double)__fdiv_rn(xc, fabsf(dn[s + u]));
             }
         }
         for (; s < job.per; ++s) {
-            float x = __ldg(base + (size_t)__ldg(ix + s) * dim);
+            float x = element(__ldg(ix + s), dn[s]);
             if (job.other_mean) x = __fsub_rn(x, mu);
-            acc += (double)__fdiv_rn(x, dn[s]);
+            acc += (double)__fdiv_rn(x, fabsf(dn[s]));
         }
     }
     job.mbar[c] = acc / (double)nsamp;
@@ -511,6 +566,11 @@ __global__ void __launch_bounds__(kFinWarps * 32, kFinCtas) k_level_finish(const
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             if (r >= nrow) break;
+            if (job.src.rows) {
+                const bool zeroed = warp_source_row<DIM>(job.src, (int64_t)o * job.n + 2 * j + r, lane, v[r]);
+                if (zeroed && lane == 0 && job.src.nan_rows) atomicAdd(job.src.nan_rows, 1);
+                continue;
+            }
             float *q = job.vecs + ((size_t)o * job.n + 2 * j + r) * DIM;
 #pragma unroll
             for (int b = 0; b < NB; ++b) v[r][b] = *reinterpret_cast<const float4 *>(q + b * 128 + 4 * lane);
@@ -720,9 +780,12 @@ extern "C" int svx_level_prologue(const SvxLevelJob *jobs_d, const SvxLevelJob *
     SVX_REQUIRE(svx_dim_supported(dim), SVX_ERR_UNSUPPORTED, "svx_level_prologue: dim %d not in {128,256,512,1024}", dim);
     if (njobs <= 0) return SVX_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int j = 0; j < njobs; ++j)
+    for (int j = 0; j < njobs; ++j) {
         SVX_REQUIRE(!jobs_h[j].idx || jobs_h[j].ko * jobs_h[j].per <= kMaxLevelSamples, SVX_ERR_UNSUPPORTED,
                     "svx_level_prologue: job %d draws %d samples (max %d)", j, jobs_h[j].ko * jobs_h[j].per, kMaxLevelSamples);
+        SVX_REQUIRE(!(jobs_h[j].src.rows || jobs_h[j].osrc.rows) || (!jobs_h[j].mean && !jobs_h[j].other_mean), SVX_ERR_ARG,
+                    "svx_level_prologue: job %d reads its rows from a source, which only the first level can (mean rows must be NULL)", j);
+    }
     for (int j0 = 0; j0 < njobs; j0 += SVX_MAX_GRID_Y) {
         const int nj = njobs - j0 < SVX_MAX_GRID_Y ? njobs - j0 : SVX_MAX_GRID_Y;
         int kmax = 0, max_samples = 0; int64_t mp = 0; bool any_mean = false, any_samples = false;

@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from . import capi
-from .engine import BatchRun, WidenJobs, host_threads, records_to_alignments
+from .engine import BatchRun, WidenJobs, host_threads, records_to_alignments, row_sources
 
 logger = logging.getLogger('vecalign')
 
@@ -299,17 +299,27 @@ def _vecalign_batch(pairs, final_alignment_types, del_percentile_frac, width_ove
         if piped and c < 4:
             st.wait_event(fork)
         with torch.cuda.stream(st):
+            sources = None
             if any(t.dtype == torch.float16 for pr in dv[lo:hi] for t in pr):
-                if piped:
-                    st.wait_event(landed[c])
-                dv[lo:hi], alive = _widen(dv[lo:hi], dev)
-                keepalive.append(alive)
+                if all(t.dtype == torch.float16 for pr in dv[lo:hi] for t in pr):
+                    # embeddings in their on-disk dtype: the level-0 prologue reads the fp16 rows itself (identity
+                    # sources: widened exactly, rows holding a NaN zeroed as make_doc_embedding does) and writes the
+                    # normalised fp32 working tensors - no widening pass over HBM
+                    sources = (row_sources([t0 for t0, _ in dv[lo:hi]]), row_sources([t1 for _, t1 in dv[lo:hi]]))
+                    keepalive.append(dv[lo:hi])
+                    dv[lo:hi] = [(torch.empty(t0.shape, dtype=torch.float32, device=dev),
+                                  torch.empty(t1.shape, dtype=torch.float32, device=dev)) for t0, t1 in dv[lo:hi]]
+                else:
+                    if piped:
+                        st.wait_event(landed[c])
+                    dv[lo:hi], alive = _widen(dv[lo:hi], dev)
+                    keepalive.append(alive)
             run = BatchRun([t0.data_ptr() for t0, _ in dv[lo:hi]], [t1.data_ptr() for _, t1 in dv[lo:hi]],
                            [t0.shape[1] for t0, _ in dv[lo:hi]], [t1.shape[1] for _, t1 in dv[lo:hi]],
                            k0, k1, dim, final_alignment_types, del_percentile_frac, width_over2, max_size_full_dp,
                            costs_sample_size, num_samps_for_norm, dev, cost_mode=_MODES[cost_mode],
                            norms0=norms0, norms1=norms1, keep_dense_csum=debug,
-                           seeds=None if seeds is None else list(seeds)[lo:hi])
+                           seeds=None if seeds is None else list(seeds)[lo:hi], sources=sources)
             _mark(f"chunk {c} planned")
             if piped:
                 st.wait_event(landed[c])

@@ -94,6 +94,15 @@ class Plan:
         capi.check(capi.lib().svx_plan_info(self.handle, capi.hptr(info)), "svx_plan_info")
         self.info = info[0]
 
+    def set_sources(self, src0, src1):
+        """svx_plan_set_sources: per-pair capi.ROW_SOURCE arrays (or None, None to clear); before bind()."""
+        if src0 is None:
+            capi.check(capi.lib().svx_plan_set_sources(self.handle, None, None), "svx_plan_set_sources")
+            return
+        self._src = (np.ascontiguousarray(src0, dtype=capi.ROW_SOURCE), np.ascontiguousarray(src1, dtype=capi.ROW_SOURCE))
+        capi.check(capi.lib().svx_plan_set_sources(self.handle, capi.hptr(self._src[0]), capi.hptr(self._src[1])),
+                   "svx_plan_set_sources")
+
     def draw(self, seeds=None):
         """The reference's RNG draws into the bound staging block: per-pair np.random.seed(seed) streams (C replay on
         the host cores this rank owns), or the global np.random stream continued and handed back."""
@@ -137,6 +146,25 @@ def workspace_bytes(params, n0, n1):
     return int(a[0]), int(h[0])
 
 
+class _SourceGather:
+    """Row sources materialised by svx_gather_doc_embedding (BatchRun with sources on the unfused prologue)."""
+
+    def __init__(self, sources, out0, out1, n0, n1, k0, k1, dim, device):
+        P = len(n0)
+        jobs = np.zeros(2 * P, dtype=capi.GATHER)
+        for p in range(P):
+            for side, (src, out, n, k) in enumerate(((sources[0][p], out0[p], n0[p], k0), (sources[1][p], out1[p], n1[p], k1))):
+                j = jobs[2 * p + side]
+                j["rows"], j["table"], j["nan_rows"], j["out"] = src["rows"], src["table"], src["nan_rows"], int(out)
+                j["k"], j["n"], j["nrows"], j["is_fp16"] = k, n, src["nrows"], src["is_fp16"]
+        self.jobs, self.dim, self.dev = jobs, int(dim), device
+        self._dev = torch.from_numpy(jobs.view(np.uint8).reshape(-1).copy()).to(device)
+
+    def run(self):
+        capi.check(capi.lib().svx_gather_doc_embedding(self._dev.data_ptr(), capi.hptr(self.jobs), len(self.jobs), self.dim,
+                                                       torch.cuda.current_stream(self.dev).cuda_stream), "svx_gather_doc_embedding")
+
+
 class WidenJobs:
     """fp16 (K, N, D) device tensors -> fp32 working tensors with one launch of svx_gather_doc_embedding (identity
     table: a widening copy that also zeroes rows containing NaNs, as make_doc_embedding does,
@@ -162,6 +190,24 @@ class WidenJobs:
                                                            torch.cuda.current_stream(self.dev).cuda_stream), "svx_gather_doc_embedding")
 
 
+def row_sources(rows, tables=None, nan_counts=None):
+    """capi.ROW_SOURCE array for a list of device row matrices: (nrows, D) tensors with a (K, N) int32 table each, or
+    (K, N, D) tensors with tables=None (identity: the tensor is the overlap tensor in its stored dtype).  fp16 or fp32.
+    nan_counts: optional int32 device tensor, one counter per entry."""
+    out = np.zeros(len(rows), dtype=capi.ROW_SOURCE)
+    for j, t in enumerate(rows):
+        if t.dtype not in (torch.float16, torch.float32) or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("row sources must be contiguous fp16 / fp32 CUDA tensors")
+        out[j]["rows"] = t.data_ptr()
+        out[j]["nrows"] = t.shape[0] if t.dim() == 2 else t.shape[0] * t.shape[1]
+        out[j]["is_fp16"] = int(t.dtype == torch.float16)
+        if tables is not None and tables[j] is not None:
+            out[j]["table"] = tables[j].data_ptr()
+        if nan_counts is not None:
+            out[j]["nan_rows"] = nan_counts.data_ptr() + 4 * j
+    return out
+
+
 def fallback_del_penalty(frac):
     """dp_utils.py:315-321: with an empty side the knob is built from [0, .5, 1] on [0, 1] (host twin of
     svx_del_knob; what svx_plan_bind presets every level's penalty to)."""
@@ -177,7 +223,11 @@ class BatchRun:
     def __init__(self, vec_ptrs0, vec_ptrs1, n0, n1, k0, k1, dim, alignment_types, del_percentile_frac,
                  width_over2, max_size_full_dp, costs_sample_size, num_samps_for_norm, device,
                  cost_mode=capi.SVX_COST_EXACT, norms0=None, norms1=None, keep_dense_csum=False, seeds=None,
-                 arena=None, fused_prologue=True):
+                 arena=None, fused_prologue=True, sources=None):
+        """vec_ptrs0 / vec_ptrs1: device (K, N, D) fp32 tensors, normalised in place.  With sources=(src0, src1)
+        (row_sources() arrays) they are pure outputs: the raw rows are read through the sources by the level-0 prologue
+        (fp16 rows and row tables never become an fp32 tensor first); a plan that needs the unfused prologue
+        materialises them with svx_gather_doc_embedding at the start of every run() instead."""
         self.P = P = len(n0)
         self.dev = device
         self.dim = dim
@@ -221,6 +271,15 @@ class BatchRun:
         # pinned staging (torch's caching host allocator recycles it): the upload below is then asynchronous,
         # so planning the next batch never waits for this batch's kernels
         self._stage = torch.empty(max(self.host_init_bytes, 16), dtype=torch.uint8, pin_memory=True)
+        self._gather = None
+        self._src_elt = 4               # bytes per element of the level-0 rows the prologue reads
+        if sources is not None:
+            if bool(info["fused_prologue"]):
+                plan.set_sources(sources[0], sources[1])
+                if len(sources[0]) and all(int(x) for x in sources[0]["is_fp16"]) and all(int(x) for x in sources[1]["is_fp16"]):
+                    self._src_elt = 2
+            else:
+                self._gather = _SourceGather(sources, vec_ptrs0, vec_ptrs1, n0, n1, k0, k1, dim, device)
         plan.bind(self.base, self._stage.data_ptr(), vec_ptrs0, vec_ptrs1)
         plan.draw(seeds)
         self._names = plan.launcher_names()
@@ -311,6 +370,8 @@ class BatchRun:
         then overlap the bandwidth- and FP32-bound kernels of the others.  Pairs are independent, so
         the result does not depend on the grouping."""
         self._events = [] if timing else None
+        if self._gather is not None:
+            self._gather.run()
         if ngroups <= 1 or self.P <= 1:
             self._pair_range = None
             self._enqueue_chain()
@@ -352,7 +413,7 @@ class BatchRun:
         for kk, nn, ko, per, want in ((K0, s0, K1, self.per1, want0), (K1, s1, K0, self.per0, want1)):
             rows = kk * nn * D * 4
             keep = np.where(l0 | keep_all, kk, min(1, kk))
-            lvl_bytes += int((rows * (1 + ~l0) + keep * nn * D * 4 + has_next * kk * (nn // 2) * D * 4 + kk * nn * 4 +
+            lvl_bytes += int((rows * np.where(l0, self._src_elt / 4.0, 2.0) + keep * nn * D * 4 + has_next * kk * (nn // 2) * D * 4 + kk * nn * 4 +
                               want * ko * per * D * 4 * 2).sum())
         norm_bytes = int((want0 * (K0 * s0 * (D * 4 + 4) + K1 * self.per1 * D * 4) +
                           want1 * (K1 * s1 * (D * 4 + 4) + K0 * self.per0 * D * 4)).sum())

@@ -382,3 +382,19 @@ def test_host_memcpy_threads(svb, nbytes, nthreads):
     assert svb.capi.lib().svx_host_memcpy(dst.ctypes.data + 32, src.ctypes.data + 32, nbytes, nthreads) == 0
     assert np.array_equal(dst[32:32 + nbytes], src[32:32 + nbytes])
     assert not dst[:32].any() and not dst[32 + nbytes:].any()
+
+
+def test_plan_sources_argument_checks(svb):
+    """svx_plan_set_sources (host only): both sides or none, every pair needs rows, and the unfused prologue refuses."""
+    from speech_vecalign_b200 import engine
+    prm = engine.make_params(4, 4, 1024, [(1, 1)], 0.2, 7, 300, 20000, 100)
+    pl = engine.Plan(prm, [10], [12])
+    src = np.zeros(1, dtype=svb.capi.ROW_SOURCE)
+    rc = svb.capi.lib().svx_plan_set_sources(pl.handle, svb.capi.hptr(src), None)
+    assert rc != 0 and "both sides" in svb.capi.lib().svx_last_error_string().decode()
+    rc = svb.capi.lib().svx_plan_set_sources(pl.handle, svb.capi.hptr(src), svb.capi.hptr(src))
+    assert rc != 0 and "no source rows" in svb.capi.lib().svx_last_error_string().decode()
+    big = engine.Plan(engine.make_params(4, 4, 1024, [(1, 1)], 0.2, 7, 300, 20000, 5000), [10], [12])
+    src["rows"] = 16
+    rc = svb.capi.lib().svx_plan_set_sources(big.handle, svb.capi.hptr(src), svb.capi.hptr(src))
+    assert rc != 0 and "unfused" in svb.capi.lib().svx_last_error_string().decode()
