@@ -591,17 +591,31 @@ __global__ void __launch_bounds__(kFinWarps * 32, kFinCtas) k_level_finish(const
             if (o >= job.keep) continue;       // only feeds the pair sum below
 #pragma unroll
             for (int b = 0; b < NB; ++b) *reinterpret_cast<float4 *>(q + b * 128 + 4 * lane) = v[r][b];
-            if (want_norms) {
-                double acc = 0.0;
+        }
+        if (want_norms && o < job.keep) {
+            // norms = 1 - row . mbar, fp64: both rows of the pair against ONE read of mbar from shared memory (8 KB per
+            // read: with a read per row this kernel's shared-memory traffic, not HBM, set its time once the level-0 rows
+            // came in as fp16); per-row accumulation order unchanged
+            double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    const double *m = mb + b * 128 + 4 * lane;
-                    acc = fma((double)v[r][b].x, m[0], acc); acc = fma((double)v[r][b].y, m[1], acc);
-                    acc = fma((double)v[r][b].z, m[2], acc); acc = fma((double)v[r][b].w, m[3], acc);
+            for (int b = 0; b < NB; ++b) {
+                const double *m = mb + b * 128 + 4 * lane;
+                const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+                acc0 = fma((double)v[0][b].x, m0, acc0); acc0 = fma((double)v[0][b].y, m1, acc0);
+                acc0 = fma((double)v[0][b].z, m2, acc0); acc0 = fma((double)v[0][b].w, m3, acc0);
+                if (nrow == 2) {
+                    acc1 = fma((double)v[1][b].x, m0, acc1); acc1 = fma((double)v[1][b].y, m1, acc1);
+                    acc1 = fma((double)v[1][b].z, m2, acc1); acc1 = fma((double)v[1][b].w, m3, acc1);
                 }
+            }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                if (lane == 0) job.norms[(size_t)o * job.n + 2 * j + r] = __fsub_rn(1.0f, (float)acc);
+            for (int off = 16; off > 0; off >>= 1) {
+                acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+                acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+            }
+            if (lane == 0) {
+                job.norms[(size_t)o * job.n + 2 * j] = __fsub_rn(1.0f, (float)acc0);
+                if (nrow == 2) job.norms[(size_t)o * job.n + 2 * j + 1] = __fsub_rn(1.0f, (float)acc1);
             }
         }
         if (job.next && j < half) {
