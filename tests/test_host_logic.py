@@ -398,3 +398,13 @@ def test_plan_sources_argument_checks(svb):
     src["rows"] = 16
     rc = svb.capi.lib().svx_plan_set_sources(big.handle, svb.capi.hptr(src), svb.capi.hptr(src))
     assert rc != 0 and "unfused" in svb.capi.lib().svx_last_error_string().decode()
+
+
+def test_row_sources_reject_host_tensors(svb):
+    """engine.row_sources describes DEVICE row matrices; a host tensor or another dtype is an error, not a silent copy."""
+    import torch
+    from speech_vecalign_b200 import engine
+    with pytest.raises(ValueError):
+        engine.row_sources([torch.zeros(4, 128, dtype=torch.float16)])
+    with pytest.raises(ValueError):
+        engine.row_sources([torch.zeros(4, 128, dtype=torch.float64)])
